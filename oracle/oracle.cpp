@@ -1,0 +1,797 @@
+// oracle/oracle.cpp
+// ============================================================================
+// TEST INFRASTRUCTURE ONLY — NOT PART OF THE PRODUCT PATH.
+//
+// CPU restatement of the semantics of LuisaCompute's CPU ("Embree") backend for
+// the ray-tracing acceleration path.  Only tests/, __graft_entry__.smoke() and
+// bench.py's cpu_baseline / --impl reference legs may load this library, and
+// only as the checker / timed CPU baseline.  The product (luisacompute_b200)
+// never links, loads or calls anything here.
+//
+// PARITY UNPINNED: the reference's real oracle is Rust + Embree 4 (crate
+// embree_sys 0.1.11, git 6a0a591d..., src/rust/Cargo.lock:266-274) and can
+// not be built in this image (no cargo/rustc, no Embree, no network).  The
+// reference ships no golden vectors for this path.  This
+// file therefore restates the *published semantics* and is pinned only by
+// (i) closed-form answers (ray/triangle, ray/sphere; tests/test_oracle.py) and
+// (ii) an O(rays x prims) brute-force mode in this same file.
+//
+// What it follows (all paths relative to /root/reference):
+//   src/rust/luisa_compute_backend_impl/src/cpu/accel.rs
+//     :284-295  instance defaults (identity affine, mask 0xff, opaque)
+//     :324-447  AccelImpl::update (modification flags, per-flag behaviour)
+//     :449-509  trace_closest (rtcIntersect1; miss = inst/prim ~0, bary 0, t=tmax)
+//     :511-535  trace_any     (rtcOccluded1)
+//     :582-800  ray_query     (filter_fn for triangles, intersect/occluded_fn
+//                              for procedural primitives; commit iff
+//                              t_near <= t < t_far :711-713,751-753)
+//   src/backends/cuda/cuda_builtin/cuda_builtin_kernels.cu:52-111 (update_accel:
+//     the CUDA flavour of the same modification semantics; default here)
+//   src/backends/cuda/cuda_builtin/cuda_device_resource.h:1783-1829 (mask & 0xff,
+//     all geometry opaque for intersect/intersect_any, procedural prims invisible)
+//   include/luisa/runtime/rtx/{ray,hit,aabb,triangle}.h (wire layouts)
+//   Embree semantics: hit iff tnear <= t <= tfar; (u,v) weights of v1,v2;
+//     instance transform applied to the ray (t is preserved).
+//
+// Divergences D1-D5 of SURVEY.md §8c: CUDA/API intent is followed:
+//   D1 opaque instances auto-commit triangles under RayQuery (no callback),
+//   D2 a miss is compared on inst only (we still write prim=~0,bary=0,t=tmax),
+//   D3/D4 masks act, 8 bits, D5 query_any is compared on hit/miss only.
+//
+// Arithmetic: inputs are fp32 (as on the wire); all geometry is evaluated in
+// double.  For every closest-hit ray the oracle also reports the 2nd-nearest
+// distinct hit t (for the 1e-5 tie rule) and offers orc_eval_hit() so a claimed
+// (inst, prim) can be evaluated exactly.
+// ============================================================================
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <thread>
+#include <vector>
+
+namespace {
+
+struct d3 {
+    double x, y, z;
+};
+inline d3 operator+(d3 a, d3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline d3 operator-(d3 a, d3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline d3 operator*(d3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+inline double dot(d3 a, d3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline d3 cross(d3 a, d3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+
+struct Box {
+    double lo[3], hi[3];
+    void reset() {
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::numeric_limits<double>::infinity();
+            hi[a] = -std::numeric_limits<double>::infinity();
+        }
+    }
+    void grow(const Box &b) {
+        for (int a = 0; a < 3; a++) {
+            lo[a] = std::min(lo[a], b.lo[a]);
+            hi[a] = std::max(hi[a], b.hi[a]);
+        }
+    }
+    void grow(d3 p) {
+        lo[0] = std::min(lo[0], p.x), hi[0] = std::max(hi[0], p.x);
+        lo[1] = std::min(lo[1], p.y), hi[1] = std::max(hi[1], p.y);
+        lo[2] = std::min(lo[2], p.z), hi[2] = std::max(hi[2], p.z);
+    }
+    double area() const {
+        double dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0) return 0;
+        return 2 * (dx * dy + dy * dz + dz * dx);
+    }
+};
+
+// ---- wire layouts (include/luisa/runtime/rtx/*.h) --------
+struct WireRay {
+    float o[3], tmin, d[3], tmax;
+};
+static_assert(sizeof(WireRay) == 32, "");
+struct WireHit {// SurfaceHit / CommittedHit share this 24-byte footprint
+    uint32_t inst, prim;
+    float u, v;
+    union {
+        struct {
+            float t;
+            uint32_t pad;
+        } s;
+        struct {
+            uint32_t hit_type;
+            float t;
+        } c;
+    };
+};
+static_assert(sizeof(WireHit) == 24, "");
+struct alignas(16) WireMod {// AccelBuildCommand::Modification, command.h:534-552
+    uint32_t index, user_id, flags, vis_mask;
+    float affine[12];
+    uint64_t primitive;
+};
+static_assert(sizeof(WireMod) == 80, "");
+
+constexpr uint32_t MOD_PRIMITIVE = 1u, MOD_TRANSFORM = 2u, MOD_OPAQUE_ON = 4u, MOD_OPAQUE_OFF = 8u,
+                   MOD_VISIBILITY = 16u, MOD_USER_ID = 32u;
+
+// ---- a plain binary BVH over boxes (binned SAH, median fallback) ------------
+struct BVH {
+    struct Node {
+        Box box;
+        uint32_t left, right;// children (internal) or first,count (leaf)
+        bool leaf;
+    };
+    std::vector<Node> nodes;
+    std::vector<uint32_t> order;// primitive permutation
+
+    void build(const std::vector<Box> &boxes) {
+        const size_t n = boxes.size();
+        nodes.clear();
+        order.resize(n);
+        for (size_t i = 0; i < n; i++) order[i] = (uint32_t)i;
+        if (n == 0) return;
+        nodes.reserve(2 * n);
+        std::vector<d3> cent(n);
+        for (size_t i = 0; i < n; i++)
+            cent[i] = {0.5 * (boxes[i].lo[0] + boxes[i].hi[0]), 0.5 * (boxes[i].lo[1] + boxes[i].hi[1]),
+                       0.5 * (boxes[i].lo[2] + boxes[i].hi[2])};
+        nodes.push_back({});
+        struct Job {
+            uint32_t node, first, count;
+        };
+        std::vector<Job> stack{{0u, 0u, (uint32_t)n}};
+        while (!stack.empty()) {
+            Job j = stack.back();
+            stack.pop_back();
+            Box b, cb;
+            b.reset(), cb.reset();
+            for (uint32_t i = j.first; i < j.first + j.count; i++) {
+                b.grow(boxes[order[i]]);
+                cb.grow(cent[order[i]]);
+            }
+            nodes[j.node].box = b;
+            if (j.count <= 2) {
+                nodes[j.node].leaf = true, nodes[j.node].left = j.first, nodes[j.node].right = j.count;
+                continue;
+            }
+            int axis = 0;
+            double ext[3] = {cb.hi[0] - cb.lo[0], cb.hi[1] - cb.lo[1], cb.hi[2] - cb.lo[2]};
+            if (ext[1] > ext[axis]) axis = 1;
+            if (ext[2] > ext[axis]) axis = 2;
+            uint32_t mid = j.first + j.count / 2;
+            bool split_done = false;
+            if (ext[axis] > 0 && j.count > 8) {
+                // binned SAH on the longest centroid axis
+                constexpr int NB = 16;
+                Box bb[NB];
+                uint32_t bc[NB] = {};
+                for (auto &x : bb) x.reset();
+                const double k = NB * (1 - 1e-9) / ext[axis];
+                auto cget = [&](uint32_t p) { return axis == 0 ? cent[p].x : axis == 1 ? cent[p].y : cent[p].z; };
+                for (uint32_t i = j.first; i < j.first + j.count; i++) {
+                    int bi = std::min(NB - 1, std::max(0, (int)((cget(order[i]) - cb.lo[axis]) * k)));
+                    bb[bi].grow(boxes[order[i]]), bc[bi]++;
+                }
+                double ra[NB];
+                Box acc;
+                acc.reset();
+                uint32_t cnt = 0;
+                for (int i = NB - 1; i > 0; i--) {
+                    acc.grow(bb[i]), cnt += bc[i];
+                    ra[i] = acc.area() * cnt;
+                }
+                acc.reset(), cnt = 0;
+                double best = std::numeric_limits<double>::infinity();
+                int bs = -1;
+                for (int i = 0; i < NB - 1; i++) {
+                    acc.grow(bb[i]), cnt += bc[i];
+                    if (cnt == 0 || cnt == j.count) continue;
+                    double c = acc.area() * cnt + ra[i + 1];
+                    if (c < best) best = c, bs = i;
+                }
+                if (bs >= 0) {
+                    auto it = std::partition(order.begin() + j.first, order.begin() + j.first + j.count, [&](uint32_t p) {
+                        int bi = std::min(NB - 1, std::max(0, (int)((cget(p) - cb.lo[axis]) * k)));
+                        return bi <= bs;
+                    });
+                    mid = (uint32_t)(it - order.begin());
+                    split_done = mid > j.first && mid < j.first + j.count;
+                }
+            }
+            if (!split_done) {
+                mid = j.first + j.count / 2;
+                auto cget = [&](uint32_t p) { return axis == 0 ? cent[p].x : axis == 1 ? cent[p].y : cent[p].z; };
+                std::nth_element(order.begin() + j.first, order.begin() + mid, order.begin() + j.first + j.count,
+                                 [&](uint32_t a, uint32_t b2) { return cget(a) < cget(b2); });
+            }
+            uint32_t l = (uint32_t)nodes.size();
+            nodes.push_back({}), nodes.push_back({});
+            nodes[j.node].leaf = false, nodes[j.node].left = l, nodes[j.node].right = l + 1;
+            stack.push_back({l, j.first, mid - j.first});
+            stack.push_back({l + 1, mid, j.first + j.count - mid});
+        }
+    }
+};
+
+// conservative slab test in double; returns entry distance or +inf
+inline bool slab(const Box &b, d3 o, d3 inv, double tmin, double tmax, double &tn) {
+    double t0 = tmin, t1 = tmax;
+    const double oo[3] = {o.x, o.y, o.z}, ii[3] = {inv.x, inv.y, inv.z};
+    for (int a = 0; a < 3; a++) {
+        double ta = (b.lo[a] - oo[a]) * ii[a], tb = (b.hi[a] - oo[a]) * ii[a];
+        if (std::isnan(ta) || std::isnan(tb)) {// 0 * inf: origin on the slab plane, direction parallel
+            if (oo[a] < b.lo[a] || oo[a] > b.hi[a]) return false;
+            continue;
+        }
+        if (ta > tb) std::swap(ta, tb);
+        // widen by a few ulps so the box test can never be stricter than the primitive test
+        ta -= std::abs(ta) * 1e-12, tb += std::abs(tb) * 1e-12;
+        t0 = std::max(t0, ta), t1 = std::min(t1, tb);
+    }
+    tn = t0;
+    return t0 <= t1;
+}
+
+enum GeomKind : uint32_t { KIND_MESH = 0, KIND_PROCEDURAL = 1 };
+
+struct Geometry {
+    GeomKind kind;
+    std::vector<d3> verts;        // mesh
+    std::vector<uint32_t> tris;   // mesh, 3 per triangle
+    std::vector<Box> boxes;       // procedural (24-byte AABB on the wire)
+    BVH bvh;
+    Box bounds;
+    bool built = false;
+};
+
+struct Instance {// accel.rs:270-295
+    double m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};// row-major 3x4, object -> world
+    double inv[12];
+    uint32_t user_id = 0, mask = 0xffu;
+    bool opaque = true;
+    const Geometry *geom = nullptr;
+};
+
+inline void invert_affine(const double *m, double *inv) {
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    const double id = 1.0 / det;
+    inv[0] = (e * i - f * h) * id, inv[1] = (c * h - b * i) * id, inv[2] = (b * f - c * e) * id;
+    inv[4] = (f * g - d * i) * id, inv[5] = (a * i - c * g) * id, inv[6] = (c * d - a * f) * id;
+    inv[8] = (d * h - e * g) * id, inv[9] = (b * g - a * h) * id, inv[10] = (a * e - b * d) * id;
+    inv[3] = -(inv[0] * m[3] + inv[1] * m[7] + inv[2] * m[11]);
+    inv[7] = -(inv[4] * m[3] + inv[5] * m[7] + inv[6] * m[11]);
+    inv[11] = -(inv[8] * m[3] + inv[9] * m[7] + inv[10] * m[11]);
+}
+inline d3 xf_point(const double *m, d3 p) {
+    return {m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7],
+            m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]};
+}
+inline d3 xf_vec(const double *m, d3 v) {
+    return {m[0] * v.x + m[1] * v.y + m[2] * v.z, m[4] * v.x + m[5] * v.y + m[6] * v.z,
+            m[8] * v.x + m[9] * v.y + m[10] * v.z};
+}
+
+struct Accel {
+    std::vector<Instance> inst;
+    BVH tlas;
+    std::vector<Box> wboxes;
+    bool built = false;
+};
+
+// double-precision ray/triangle. Double-sided, no culling (cuda_mesh.cpp:15-16).
+// (u, v) are the weights of v1, v2 (hit.h:30-37, src/dsl/rtx/hit.cpp:7-20).
+// `slack` widens the inside test (used only by orc_eval_hit; 0 for tracing).
+inline bool tri_hit(d3 o, d3 d, d3 v0, d3 v1, d3 v2, double slack, double &t, double &u, double &v) {
+    const d3 A = v0 - o, B = v1 - o, C = v2 - o;
+    // scalar triple products: weights of v0, v1, v2
+    const double U = dot(d, cross(B, C)), V = dot(d, cross(C, A)), W = dot(d, cross(A, B));
+    const double det = U + V + W;
+    if (det == 0.0) return false;
+    const double id = 1.0 / det;
+    const double b0 = U * id, b1 = V * id, b2 = W * id;
+    if (b0 < -slack || b1 < -slack || b2 < -slack) return false;
+    const d3 n = cross(v1 - v0, v2 - v0);
+    const double dn = dot(d, n);
+    if (dn == 0.0) return false;
+    t = dot(A, n) / dn;
+    u = b1, v = b2;
+    return true;
+}
+
+struct ClosestResult {
+    uint32_t inst = ~0u, prim = ~0u;
+    double t = 0, u = 0, v = 0;
+    double t2 = std::numeric_limits<double>::infinity();// 2nd nearest hit on a different (inst, prim)
+    uint64_t nodes = 0, tris = 0;
+};
+
+struct QueryCallbacks;// fwd
+
+// ---- RayQuery state (cpu_resource.h:288-396, accel.rs:582-800) ---------------
+enum HitType : uint32_t { HIT_MISS = 0, HIT_SURFACE = 1, HIT_PROCEDURAL = 2 };
+
+// Built-in candidate programs shared with the device side (luisacompute_b200/csrc/
+// lcrt_query_programs.cuh implements the same rules in fp32).
+enum TriProgram : uint32_t {
+    TRI_COMMIT_ALL = 0,     // on_surface_candidate: always commit
+    TRI_CUTOUT_MOD3 = 1,    // commit iff prim % 3 != 0         (alpha cut-out stand-in)
+    TRI_IGNORE_ALL = 2,     // never commit
+    TRI_TERMINATE_FIRST = 3,// commit + terminate
+};
+enum ProcProgram : uint32_t {
+    PROC_SPHERE = 0,        // sphere inscribed in the AABB (test_procedural.cpp:101-125 pattern)
+    PROC_BOX = 1,           // the AABB itself (slab entry distance)
+    PROC_IGNORE_ALL = 2,
+};
+
+struct Tracer {
+    const Accel *accel;
+
+    // generic two-level traversal; F is called for every (instance, primitive) whose box the ray enters
+    template<class LeafFn>
+    void walk_blas(const Geometry &g, d3 o, d3 d, double tmin, double &tmax, LeafFn &&leaf, uint64_t *nodes) const {
+        if (g.bvh.nodes.empty()) return;
+        const d3 inv = {1.0 / d.x, 1.0 / d.y, 1.0 / d.z};
+        uint32_t stack[128];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const auto &n = g.bvh.nodes[stack[--sp]];
+            double tn;
+            if (nodes) (*nodes)++;
+            if (!slab(n.box, o, inv, tmin, tmax, tn)) continue;
+            if (n.leaf) {
+                for (uint32_t i = 0; i < n.right; i++)
+                    if (!leaf(g.bvh.order[n.left + i])) return;
+            } else {
+                double tl, tr;
+                const bool hl = slab(g.bvh.nodes[n.left].box, o, inv, tmin, tmax, tl);
+                const bool hr = slab(g.bvh.nodes[n.right].box, o, inv, tmin, tmax, tr);
+                if (hl && hr) {
+                    if (tl < tr) stack[sp++] = n.right, stack[sp++] = n.left;
+                    else stack[sp++] = n.left, stack[sp++] = n.right;
+                } else if (hl) stack[sp++] = n.left;
+                else if (hr) stack[sp++] = n.right;
+            }
+        }
+    }
+
+    template<class InstFn>
+    void walk_tlas(d3 o, d3 d, double tmin, const double &tmax, InstFn &&fn, uint64_t *nodes) const {
+        if (accel->tlas.nodes.empty()) return;
+        const d3 inv = {1.0 / d.x, 1.0 / d.y, 1.0 / d.z};
+        uint32_t stack[128];
+        int sp = 0;
+        stack[sp++] = 0;
+        while (sp) {
+            const auto &n = accel->tlas.nodes[stack[--sp]];
+            double tn;
+            if (nodes) (*nodes)++;
+            if (!slab(n.box, o, inv, tmin, tmax, tn)) continue;
+            if (n.leaf) {
+                for (uint32_t i = 0; i < n.right; i++)
+                    if (!fn(accel->tlas.order[n.left + i])) return;
+            } else {
+                double tl, tr;
+                const bool hl = slab(accel->tlas.nodes[n.left].box, o, inv, tmin, tmax, tl);
+                const bool hr = slab(accel->tlas.nodes[n.right].box, o, inv, tmin, tmax, tr);
+                if (hl && hr) {
+                    if (tl < tr) stack[sp++] = n.right, stack[sp++] = n.left;
+                    else stack[sp++] = n.left, stack[sp++] = n.right;
+                } else if (hl) stack[sp++] = n.left;
+                else if (hr) stack[sp++] = n.right;
+            }
+        }
+    }
+
+    // intersect(): nearest triangle hit; procedural primitives are invisible
+    // (cuda_device_resource.h:1818-1822, accel.rs:449-509)
+    ClosestResult closest(const WireRay &r, uint32_t mask, bool brute) const {
+        ClosestResult res;
+        const d3 o = {r.o[0], r.o[1], r.o[2]}, d = {r.d[0], r.d[1], r.d[2]};
+        const double tmin = r.tmin;
+        double tmax = r.tmax;    // nearest
+        double bound = r.tmax;   // pruning bound = 2nd nearest so far (so that t2 is exact)
+        bool have = false;
+        auto visit_inst = [&](uint32_t ii) -> bool {
+            const Instance &in = accel->inst[ii];
+            if (!in.geom || in.geom->kind != KIND_MESH) return true;
+            if (((in.mask & mask) & 0xffu) == 0) return true;
+            const d3 lo = xf_point(in.inv, o), ld = xf_vec(in.inv, d);
+            const Geometry &g = *in.geom;
+            auto on_tri = [&](uint32_t p) -> bool {
+                res.tris++;
+                double t, u, v;
+                if (!tri_hit(lo, ld, g.verts[g.tris[3 * p]], g.verts[g.tris[3 * p + 1]], g.verts[g.tris[3 * p + 2]], 0.0, t, u, v))
+                    return true;
+                if (t < tmin || t > r.tmax) return true;// Embree: tnear <= t <= tfar
+                if (!have || t < res.t) {
+                    if (have) res.t2 = res.t;
+                    res.t = t, res.u = u, res.v = v, res.inst = ii, res.prim = p, have = true;
+                } else if (t < res.t2) {
+                    res.t2 = t;
+                }
+                bound = std::min<double>(r.tmax, res.t2);
+                return true;
+            };
+            if (brute) {
+                for (uint32_t p = 0; p < g.tris.size() / 3; p++) on_tri(p);
+            } else {
+                walk_blas(g, lo, ld, tmin, bound, on_tri, &res.nodes);
+            }
+            return true;
+        };
+        if (brute) {
+            for (uint32_t i = 0; i < accel->inst.size(); i++) visit_inst(i);
+        } else {
+            walk_tlas(o, d, tmin, bound, visit_inst, &res.nodes);
+        }
+        (void)tmax;
+        if (!have) res.t = r.tmax;
+        return res;
+    }
+
+    // intersect_any(): (accel.rs:511-535)
+    bool any(const WireRay &r, uint32_t mask, bool brute) const {
+        const d3 o = {r.o[0], r.o[1], r.o[2]}, d = {r.d[0], r.d[1], r.d[2]};
+        const double tmin = r.tmin;
+        double tmax = r.tmax;
+        bool hit = false;
+        auto visit_inst = [&](uint32_t ii) -> bool {
+            const Instance &in = accel->inst[ii];
+            if (!in.geom || in.geom->kind != KIND_MESH) return true;
+            if (((in.mask & mask) & 0xffu) == 0) return true;
+            const d3 lo = xf_point(in.inv, o), ld = xf_vec(in.inv, d);
+            const Geometry &g = *in.geom;
+            auto on_tri = [&](uint32_t p) -> bool {
+                double t, u, v;
+                if (!tri_hit(lo, ld, g.verts[g.tris[3 * p]], g.verts[g.tris[3 * p + 1]], g.verts[g.tris[3 * p + 2]], 0.0, t, u, v))
+                    return true;
+                if (t < tmin || t > tmax) return true;
+                hit = true;
+                return false;
+            };
+            if (brute) {
+                for (uint32_t p = 0; p < g.tris.size() / 3 && !hit; p++) on_tri(p);
+            } else {
+                walk_blas(g, lo, ld, tmin, tmax, on_tri, nullptr);
+            }
+            return !hit;
+        };
+        if (brute) {
+            for (uint32_t i = 0; i < accel->inst.size() && !hit; i++) visit_inst(i);
+        } else {
+            walk_tlas(o, d, tmin, tmax, visit_inst, nullptr);
+        }
+        return hit;
+    }
+
+    // RayQuery (query_all / query_any) with the built-in candidate programs.
+    // Semantics (CUDA flavour, D1): triangles of opaque instances are committed without
+    // a callback; triangles of non-opaque instances go through the triangle program;
+    // procedural primitives always go through the procedural program; a procedural
+    // commit is accepted iff tmin <= t < current tmax (accel.rs:711-713,751-753).
+    // Candidates further than the committed hit are never presented (tmax shrinks).
+    WireHit query(const WireRay &r, uint32_t mask, bool terminate_on_first, uint32_t tri_prog, uint32_t proc_prog,
+                  bool brute) const {
+        WireHit h{};
+        h.inst = ~0u, h.prim = ~0u, h.u = 0, h.v = 0, h.c.hit_type = HIT_MISS, h.c.t = r.tmax;
+        const d3 o = {r.o[0], r.o[1], r.o[2]}, d = {r.d[0], r.d[1], r.d[2]};
+        const double tmin = r.tmin;
+        double tmax = r.tmax;
+        bool done = false;
+        // closest semantics need the *nearest committed* candidate irrespective of traversal order:
+        // since programs here are order-independent (pure functions of ids / geometry), we simply
+        // keep the nearest committed candidate.  "terminate" stops the traversal (first found).
+        auto visit_inst = [&](uint32_t ii) -> bool {
+            const Instance &in = accel->inst[ii];
+            if (!in.geom) return true;
+            if (((in.mask & mask) & 0xffu) == 0) return true;
+            const d3 lo = xf_point(in.inv, o), ld = xf_vec(in.inv, d);
+            const Geometry &g = *in.geom;
+            if (g.kind == KIND_MESH) {
+                auto on_tri = [&](uint32_t p) -> bool {
+                    double t, u, v;
+                    if (!tri_hit(lo, ld, g.verts[g.tris[3 * p]], g.verts[g.tris[3 * p + 1]], g.verts[g.tris[3 * p + 2]], 0.0, t, u, v))
+                        return true;
+                    if (t < tmin || t > tmax) return true;
+                    bool commit = true, term = false;
+                    if (!in.opaque) {
+                        switch (tri_prog) {
+                            case TRI_COMMIT_ALL: break;
+                            case TRI_CUTOUT_MOD3: commit = (p % 3u) != 0u; break;
+                            case TRI_IGNORE_ALL: commit = false; break;
+                            case TRI_TERMINATE_FIRST: term = true; break;
+                        }
+                    }
+                    if (commit) {
+                        tmax = t;
+                        h.inst = ii, h.prim = p, h.u = (float)u, h.v = (float)v, h.c.hit_type = HIT_SURFACE, h.c.t = (float)t;
+                        if (terminate_on_first || term) done = true;
+                    }
+                    return !done;
+                };
+                if (brute) {
+                    for (uint32_t p = 0; p < g.tris.size() / 3 && !done; p++) on_tri(p);
+                } else {
+                    walk_blas(g, lo, ld, tmin, tmax, on_tri, nullptr);
+                }
+            } else {
+                auto on_box = [&](uint32_t p) -> bool {
+                    const Box &b = g.boxes[p];
+                    // candidate is presented iff the (object-space) ray enters the AABB within [tmin, tmax]
+                    const d3 inv = {1.0 / ld.x, 1.0 / ld.y, 1.0 / ld.z};
+                    double tn;
+                    if (!slab(b, lo, inv, tmin, tmax, tn)) return true;
+                    bool commit = false;
+                    double t = 0;
+                    switch (proc_prog) {
+                        case PROC_SPHERE: {
+                            // object-space sphere inscribed in the box, moved to world space by the
+                            // instance transform (uniform scale assumed, as in test_procedural.cpp:101-125)
+                            const d3 c_obj = {0.5 * (b.lo[0] + b.hi[0]), 0.5 * (b.lo[1] + b.hi[1]), 0.5 * (b.lo[2] + b.hi[2])};
+                            const double r_obj = 0.5 * (b.hi[0] - b.lo[0]);
+                            const d3 c = xf_point(in.m, c_obj);
+                            const d3 col0 = {in.m[0], in.m[4], in.m[8]};
+                            const double rad = r_obj * std::sqrt(dot(col0, col0));
+                            const d3 L = o - c;
+                            const double a = dot(d, d), hb = dot(L, d), cc = dot(L, L) - rad * rad;
+                            const double disc = hb * hb - a * cc;
+                            if (disc >= 0) {
+                                const double sq = std::sqrt(disc);
+                                double t0 = (-hb - sq) / a, t1 = (-hb + sq) / a;
+                                if (t0 >= tmin && t0 < tmax) commit = true, t = t0;
+                                else if (t1 >= tmin && t1 < tmax) commit = true, t = t1;
+                            }
+                            break;
+                        }
+                        case PROC_BOX: {
+                            if (tn >= tmin && tn < tmax) commit = true, t = tn;
+                            break;
+                        }
+                        default: break;
+                    }
+                    if (commit) {
+                        tmax = t;
+                        h.inst = ii, h.prim = p, h.u = 0, h.v = 0, h.c.hit_type = HIT_PROCEDURAL, h.c.t = (float)t;
+                        if (terminate_on_first) done = true;
+                    }
+                    return !done;
+                };
+                if (brute) {
+                    for (uint32_t p = 0; p < g.boxes.size() && !done; p++) on_box(p);
+                } else {
+                    walk_blas(g, lo, ld, tmin, tmax, on_box, nullptr);
+                }
+            }
+            return !done;
+        };
+        if (brute) {
+            for (uint32_t i = 0; i < accel->inst.size() && !done; i++) visit_inst(i);
+        } else {
+            walk_tlas(o, d, tmin, tmax, visit_inst, nullptr);
+        }
+        return h;
+    }
+};
+
+template<class F>
+void parallel_chunks(uint64_t n, int threads, F &&f) {
+    // 65536-ray chunks handed out by an atomic counter — the scheme of the reference's CPU
+    // dispatcher (src/rust/luisa_compute_backend_impl/src/cpu/stream.rs:185-210).
+    constexpr uint64_t CH = 65536;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (threads <= 0) threads = 1;
+    const uint64_t nchunks = (n + CH - 1) / CH;
+    threads = (int)std::min<uint64_t>(threads, std::max<uint64_t>(1, nchunks));
+    std::atomic<uint64_t> next{0};
+    auto work = [&] {
+        for (;;) {
+            uint64_t c = next.fetch_add(1);
+            if (c >= nchunks) break;
+            f(c * CH, std::min(n, (c + 1) * CH));
+        }
+    };
+    if (threads == 1) {
+        work();
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int i = 0; i < threads; i++) pool.emplace_back(work);
+    for (auto &t : pool) t.join();
+}
+
+}// namespace
+
+extern "C" {
+
+int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+// ---- geometry (GeometryImpl::build_mesh accel.rs:205-260 / build_procedural :84-141) ----
+void *orc_mesh_create(const void *vertices, uint64_t vertex_stride, uint32_t vertex_count, const uint32_t *tris,
+                      uint32_t tri_count) {
+    auto g = new Geometry;
+    g->kind = KIND_MESH;
+    g->verts.resize(vertex_count);
+    for (uint32_t i = 0; i < vertex_count; i++) {
+        const float *p = reinterpret_cast<const float *>(static_cast<const char *>(vertices) + i * vertex_stride);
+        g->verts[i] = {p[0], p[1], p[2]};
+    }
+    g->tris.assign(tris, tris + 3ull * tri_count);
+    std::vector<Box> boxes(tri_count);
+    g->bounds.reset();
+    for (uint32_t t = 0; t < tri_count; t++) {
+        boxes[t].reset();
+        for (int k = 0; k < 3; k++) boxes[t].grow(g->verts[tris[3 * t + k]]);
+        g->bounds.grow(boxes[t]);
+    }
+    g->bvh.build(boxes);
+    g->built = true;
+    return g;
+}
+
+void *orc_procedural_create(const float *aabbs, uint32_t count) {
+    auto g = new Geometry;
+    g->kind = KIND_PROCEDURAL;
+    g->boxes.resize(count);
+    g->bounds.reset();
+    for (uint32_t i = 0; i < count; i++) {
+        for (int a = 0; a < 3; a++) g->boxes[i].lo[a] = aabbs[6 * i + a], g->boxes[i].hi[a] = aabbs[6 * i + 3 + a];
+        g->bounds.grow(g->boxes[i]);
+    }
+    g->bvh.build(g->boxes);
+    g->built = true;
+    return g;
+}
+
+void orc_geometry_destroy(void *g) { delete static_cast<Geometry *>(g); }
+
+// ---- accel (AccelImpl::update accel.rs:324-447; CUDA flavour cuda_builtin_kernels.cu:52-111) ----
+void *orc_accel_create() { return new Accel; }
+void orc_accel_destroy(void *a) { delete static_cast<Accel *>(a); }
+
+// mods[i].primitive must hold a pointer returned by orc_mesh_create / orc_procedural_create.
+// cpu_flavour != 0 reproduces accel.rs:356-377 (a PRIMITIVE mod resets mask/opaque and always takes affine).
+int orc_accel_update(void *accel, uint32_t instance_count, const void *mods_, uint32_t n_mods, int update_instance_buffer_only,
+                     int cpu_flavour) {
+    auto a = static_cast<Accel *>(accel);
+    if (instance_count == 0) return -1;// cuda_accel.cpp:159
+    a->inst.resize(instance_count);
+    const WireMod *mods = static_cast<const WireMod *>(mods_);
+    for (uint32_t k = 0; k < n_mods; k++) {
+        const WireMod &m = mods[k];
+        if (m.index >= instance_count) return -2;
+        Instance &in = a->inst[m.index];
+        if (m.flags & MOD_PRIMITIVE) {
+            in.geom = reinterpret_cast<const Geometry *>(m.primitive);
+            if (!in.geom || !in.geom->built) return -3;// accel.rs:352-354 "Mesh not built"
+            if (cpu_flavour) {
+                for (int i = 0; i < 12; i++) in.m[i] = m.affine[i];
+                in.mask = 0xffu, in.opaque = true, in.user_id = m.user_id;
+            }
+            // ProceduralPrimitive instances are always non-opaque (src/runtime/rtx/accel.cpp:154-157);
+            // their opacity is irrelevant here because procedural candidates always call the program.
+        }
+        if (m.flags & MOD_OPAQUE_ON) in.opaque = true;
+        else if (m.flags & MOD_OPAQUE_OFF) in.opaque = false;
+        if (m.flags & MOD_TRANSFORM)
+            for (int i = 0; i < 12; i++) in.m[i] = m.affine[i];
+        if (m.flags & MOD_VISIBILITY) in.mask = m.vis_mask;
+        if (m.flags & MOD_USER_ID) in.user_id = m.user_id;
+    }
+    if (update_instance_buffer_only) return 0;// accel.rs:428-430
+    a->wboxes.assign(instance_count, Box{});
+    for (uint32_t i = 0; i < instance_count; i++) {
+        Instance &in = a->inst[i];
+        invert_affine(in.m, in.inv);
+        Box b;
+        b.reset();
+        if (in.geom) {
+            const Box &g = in.geom->bounds;
+            for (int c = 0; c < 8; c++) {
+                d3 p = {(c & 1) ? g.hi[0] : g.lo[0], (c & 2) ? g.hi[1] : g.lo[1], (c & 4) ? g.hi[2] : g.lo[2]};
+                b.grow(xf_point(in.m, p));
+            }
+            // pad against the rounding of the inverse transform
+            for (int ax = 0; ax < 3; ax++) {
+                double e = 1e-9 * (std::abs(b.lo[ax]) + std::abs(b.hi[ax]) + (b.hi[ax] - b.lo[ax]));
+                b.lo[ax] -= e, b.hi[ax] += e;
+            }
+        } else {
+            for (int ax = 0; ax < 3; ax++) b.lo[ax] = b.hi[ax] = 0;
+        }
+        a->wboxes[i] = b;
+    }
+    a->tlas.build(a->wboxes);
+    a->built = true;
+    return 0;
+}
+
+void orc_accel_set_instance(void *accel, uint32_t index, const float *affine12, int set_mask, uint32_t mask, int set_opaque,
+                            int opaque, int set_user_id, uint32_t user_id) {
+    // in-kernel lc_accel_set_instance_* (cuda_device_resource.h:1470-1510); takes effect at the next update
+    auto a = static_cast<Accel *>(accel);
+    Instance &in = a->inst[index];
+    if (affine12)
+        for (int i = 0; i < 12; i++) in.m[i] = affine12[i];
+    if (set_mask) in.mask = mask & 0xffu;
+    if (set_opaque && in.geom && in.geom->kind == KIND_MESH) in.opaque = opaque != 0;
+    if (set_user_id) in.user_id = user_id;
+}
+
+uint32_t orc_accel_instance_user_id(void *accel, uint32_t index) { return static_cast<Accel *>(accel)->inst[index].user_id; }
+
+// ---- tracing -----------------------------------------------------------------------------------
+// masks: per-ray array if mask_stride != 0, else masks[0] for all rays.
+// hits: 24-byte SurfaceHit records.  t2 (optional): 2nd-nearest distinct hit t (inf if none).
+// counters (optional, 2 x u64): total BVH2 nodes visited, triangles tested.
+void orc_trace_closest(void *accel, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, void *hits_, double *t2,
+                       double *t_exact, int threads, int brute, uint64_t *counters) {
+    Tracer tr{static_cast<Accel *>(accel)};
+    const WireRay *rays = static_cast<const WireRay *>(rays_);
+    WireHit *hits = static_cast<WireHit *>(hits_);
+    std::atomic<uint64_t> cn{0}, ct{0};
+    parallel_chunks(n, threads, [&](uint64_t b, uint64_t e) {
+        uint64_t ln = 0, lt = 0;
+        for (uint64_t i = b; i < e; i++) {
+            ClosestResult r = tr.closest(rays[i], mask_stride ? masks[i] : masks[0], brute != 0);
+            WireHit h{};
+            h.inst = r.inst, h.prim = r.prim, h.u = (float)r.u, h.v = (float)r.v, h.s.t = (float)r.t, h.s.pad = 0;
+            hits[i] = h;
+            if (t2) t2[i] = r.t2;
+            if (t_exact) t_exact[i] = r.t;
+            ln += r.nodes, lt += r.tris;
+        }
+        cn += ln, ct += lt;
+    });
+    if (counters) counters[0] = cn, counters[1] = ct;
+}
+
+void orc_trace_any(void *accel, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, uint8_t *out, int threads,
+                   int brute) {
+    Tracer tr{static_cast<Accel *>(accel)};
+    const WireRay *rays = static_cast<const WireRay *>(rays_);
+    parallel_chunks(n, threads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; i++) out[i] = tr.any(rays[i], mask_stride ? masks[i] : masks[0], brute != 0) ? 1 : 0;
+    });
+}
+
+// RayQuery with built-in programs; hits are 24-byte CommittedHit records.
+void orc_query(void *accel, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, int terminate_on_first,
+               uint32_t tri_prog, uint32_t proc_prog, void *hits_, int threads, int brute) {
+    Tracer tr{static_cast<Accel *>(accel)};
+    const WireRay *rays = static_cast<const WireRay *>(rays_);
+    WireHit *hits = static_cast<WireHit *>(hits_);
+    parallel_chunks(n, threads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; i++)
+            hits[i] = tr.query(rays[i], mask_stride ? masks[i] : masks[0], terminate_on_first != 0, tri_prog, proc_prog, brute != 0);
+    });
+}
+
+// Evaluate a *claimed* (inst, prim) triangle hit exactly: out = {t, u, v, min_bary}; returns 1 if the
+// supporting plane is hit at all (det != 0), 0 otherwise.  The parity tests use it to apply the tie rule
+// to N-way ties (a vertex shared by six triangles) where the 2nd-nearest t alone is not enough.
+int orc_eval_hit(void *accel, const void *ray_, uint32_t inst, uint32_t prim, double *out) {
+    auto a = static_cast<Accel *>(accel);
+    const WireRay &r = *static_cast<const WireRay *>(ray_);
+    if (inst >= a->inst.size()) return 0;
+    const Instance &in = a->inst[inst];
+    if (!in.geom || in.geom->kind != KIND_MESH || prim >= in.geom->tris.size() / 3) return 0;
+    const Geometry &g = *in.geom;
+    const d3 o = {r.o[0], r.o[1], r.o[2]}, d = {r.d[0], r.d[1], r.d[2]};
+    const d3 lo = xf_point(in.inv, o), ld = xf_vec(in.inv, d);
+    double t, u, v;
+    if (!tri_hit(lo, ld, g.verts[g.tris[3 * prim]], g.verts[g.tris[3 * prim + 1]], g.verts[g.tris[3 * prim + 2]], 1e30, t, u, v))
+        return 0;
+    out[0] = t, out[1] = u, out[2] = v, out[3] = std::min({u, v, 1.0 - u - v});
+    return 1;
+}
+
+}// extern "C"
