@@ -1,0 +1,516 @@
+// lcrt_build.h — per-thread builder functions (host+device portable): primitive bounds, Morton codes, agglomerative
+// LBVH (Apetrei 2014) with SAH leaf marking, collapse to the compressed BVH8 layout, refit.
+//
+// Replaces optixAccelBuild / optixAccelCompact as called by the reference
+// (src/backends/cuda/cuda_primitive.cpp:20-132, src/backends/cuda/cuda_accel.cpp:26-142).
+// The __global__ wrappers live in lcrt_kernels.cu; tests/hostsim runs the same functions serially on the CPU.
+#pragma once
+#include "lcrt_common.h"
+
+namespace lcrt {
+
+#if defined(__CUDA_ARCH__)
+#define LCRT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define LCRT_FENCE() __threadfence()
+#define LCRT_VOLATILE_LOAD_U32(p) (*reinterpret_cast<const volatile uint32_t *>(p))
+#else
+inline uint32_t host_atomic_add(uint32_t *p, uint32_t v) {
+    uint32_t o = *p;
+    *p += v;
+    return o;
+}
+#define LCRT_ATOMIC_ADD(p, v) ::lcrt::host_atomic_add((p), (v))
+#define LCRT_FENCE() ((void)0)
+#define LCRT_VOLATILE_LOAD_U32(p) (*(p))
+#endif
+
+constexpr uint32_t INVALID_U32 = 0xffffffffu;
+constexpr uint32_t LEAF_MARK = 0x80000000u;
+
+// ------------------------------------------------------------------------------------------ build inputs
+struct TriInput {
+    const char *verts;
+    uint64_t stride;
+    const uint32_t *tris;
+    uint32_t n;
+    static constexpr uint32_t kind = KIND_TRIANGLES;
+    static constexpr uint32_t rec_bytes = sizeof(TriRecord);
+    static constexpr uint32_t max_leaf = 3;
+    LCRT_HD void fetch(uint32_t i, float v[9]) const {
+        const uint32_t i0 = tris[3 * (uint64_t)i], i1 = tris[3 * (uint64_t)i + 1], i2 = tris[3 * (uint64_t)i + 2];
+        const float *a = reinterpret_cast<const float *>(verts + i0 * stride);
+        const float *b = reinterpret_cast<const float *>(verts + i1 * stride);
+        const float *c = reinterpret_cast<const float *>(verts + i2 * stride);
+        v[0] = a[0], v[1] = a[1], v[2] = a[2], v[3] = b[0], v[4] = b[1], v[5] = b[2], v[6] = c[0], v[7] = c[1], v[8] = c[2];
+    }
+    LCRT_HD Box box(uint32_t i) const {
+        float v[9];
+        fetch(i, v);
+        Box b = box_empty();
+        box_grow(b, v[0], v[1], v[2]), box_grow(b, v[3], v[4], v[5]), box_grow(b, v[6], v[7], v[8]);
+        return b;
+    }
+    LCRT_HD void write(char *dst, uint32_t i) const {
+        float v[9];
+        fetch(i, v);
+        f4 *d = reinterpret_cast<f4 *>(dst);
+        d[0] = make_f4(v[0], v[1], v[2], as_float(i));
+        d[1] = make_f4(v[3], v[4], v[5], 0.f);
+        d[2] = make_f4(v[6], v[7], v[8], 0.f);
+    }
+    LCRT_HD static uint32_t record_prim(const char *rec) { return as_uint(reinterpret_cast<const f4 *>(rec)->w); }
+};
+
+struct AabbInput {
+    const float *aabbs;// 24-byte records (include/luisa/runtime/rtx/aabb.h:7-10)
+    uint32_t n;
+    static constexpr uint32_t kind = KIND_AABBS;
+    static constexpr uint32_t rec_bytes = sizeof(BoxRecord);
+    static constexpr uint32_t max_leaf = 2;
+    LCRT_HD Box box(uint32_t i) const {
+        const float *p = aabbs + 6 * (uint64_t)i;
+        Box b;
+        for (int a = 0; a < 3; a++) b.lo[a] = p[a], b.hi[a] = p[3 + a];
+        return b;
+    }
+    LCRT_HD void write(char *dst, uint32_t i) const {
+        const float *p = aabbs + 6 * (uint64_t)i;
+        f4 *d = reinterpret_cast<f4 *>(dst);
+        d[0] = make_f4(p[0], p[1], p[2], as_float(i));
+        d[1] = make_f4(p[3], p[4], p[5], 0.f);
+    }
+    LCRT_HD static uint32_t record_prim(const char *rec) { return as_uint(reinterpret_cast<const f4 *>(rec)->w); }
+};
+
+LCRT_HD bool invert_affine(const float *m, double *inv) {
+    const double a = m[0], b = m[1], c = m[2], d = m[4], e = m[5], f = m[6], g = m[8], h = m[9], i = m[10];
+    const double det = a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g);
+    if (det == 0.0 || det != det) return false;
+    const double id = 1.0 / det;
+    inv[0] = (e * i - f * h) * id, inv[1] = (c * h - b * i) * id, inv[2] = (b * f - c * e) * id;
+    inv[4] = (f * g - d * i) * id, inv[5] = (a * i - c * g) * id, inv[6] = (c * d - a * f) * id;
+    inv[8] = (d * h - e * g) * id, inv[9] = (b * g - a * h) * id, inv[10] = (a * e - b * d) * id;
+    inv[3] = -(inv[0] * m[3] + inv[1] * m[7] + inv[2] * m[11]);
+    inv[7] = -(inv[4] * m[3] + inv[5] * m[7] + inv[6] * m[11]);
+    inv[11] = -(inv[8] * m[3] + inv[9] * m[7] + inv[10] * m[11]);
+    return true;
+}
+
+struct InstInput {
+    const Instance *inst;
+    uint32_t n;
+    static constexpr uint32_t kind = KIND_INSTANCES;
+    static constexpr uint32_t rec_bytes = sizeof(InstanceRecord);
+    static constexpr uint32_t max_leaf = 1;
+    LCRT_HD static const BlobHeader *blas_of(const Instance &in) {
+        const BlobHeader *h = reinterpret_cast<const BlobHeader *>(in.handle);
+        if (h == nullptr || h->magic != BLOB_MAGIC || !h->built || h->kind == KIND_INSTANCES) return nullptr;
+        return h;
+    }
+    LCRT_HD Box box(uint32_t i) const {
+        const Instance in = inst[i];
+        const BlobHeader *h = blas_of(in);
+        Box b = box_empty();
+        if (h == nullptr || !(h->lo[0] <= h->hi[0])) return b;
+        double tmp[12];
+        if (!invert_affine(in.affine, tmp)) return b;// singular transform: the instance can not be hit
+        const float *m = in.affine;
+        for (int c = 0; c < 8; c++) {
+            const double x = (c & 1) ? h->hi[0] : h->lo[0], y = (c & 2) ? h->hi[1] : h->lo[1], z = (c & 4) ? h->hi[2] : h->lo[2];
+            const double wx = m[0] * x + m[1] * y + m[2] * z + m[3], wy = m[4] * x + m[5] * y + m[6] * z + m[7],
+                         wz = m[8] * x + m[9] * y + m[10] * z + m[11];
+            box_grow(b, (float)wx, (float)wy, (float)wz);
+        }
+        // pad: the ray is moved to object space with an fp32 inverse, so the world box must cover that rounding
+        for (int a = 0; a < 3; a++) {
+            const float e = 2e-6f * (fmaxf(fabsf(b.lo[a]), fabsf(b.hi[a])) + (b.hi[a] - b.lo[a])) + 1e-30f;
+            b.lo[a] -= e, b.hi[a] += e;
+        }
+        return b;
+    }
+    LCRT_HD void write(char *dst, uint32_t i) const {
+        const Instance in = inst[i];
+        const BlobHeader *h = blas_of(in);
+        InstanceRecord r;
+        if (!invert_affine(in.affine, r.inv)) {
+            for (int k = 0; k < 12; k++) r.inv[k] = 0.0;
+        }
+        r.nodes = h ? (uint64_t)(reinterpret_cast<const char *>(h) + h->nodes_offset) : 0ull;
+        r.prims = h ? (uint64_t)(reinterpret_cast<const char *>(h) + h->prims_offset) : 0ull;
+        r.inst = i;
+        r.mask = h ? (in.mask & 0xffu) : 0u;// an unbound instance can never be entered
+        const bool opaque = !(in.flags & INSTANCE_FLAG_ENFORCE_ANYHIT);
+        r.flags = (h ? h->kind : KIND_TRIANGLES) | (opaque ? IREC_OPAQUE : 0u);
+        r.pad = 0u;
+        copy_vec16(dst, &r, 8);
+    }
+    LCRT_HD static uint32_t record_prim(const char *rec) { return reinterpret_cast<const InstanceRecord *>(rec)->inst; }
+};
+
+// ------------------------------------------------------------------------------------------ scene bounds / Morton
+// order-preserving float <-> uint map so that atomicMin / atomicMax on uints reduce floats
+LCRT_HD uint32_t float_to_ordered(float f) {
+    const uint32_t u = as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+LCRT_HD float ordered_to_float(uint32_t u) { return as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
+
+LCRT_HD uint64_t expand_bits_21(uint64_t v) {// spread the low 21 bits to every third bit
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+// 63-bit Morton code of the box centre relative to the centroid bounds [clo, chi]
+LCRT_HD uint64_t morton63(const Box &b, const float clo[3], const float inv_ext[3]) {
+    uint64_t code = 0;
+    for (int a = 0; a < 3; a++) {
+        const float c = 0.5f * (b.lo[a] + b.hi[a]);
+        float f = (c - clo[a]) * inv_ext[a];// [0, 1]
+        if (!(f >= 0.f)) f = 0.f;           // also catches NaN (empty boxes)
+        if (f > 1.f) f = 1.f;
+        uint32_t q = (uint32_t)(f * 2097152.0f);
+        if (q > 2097151u) q = 2097151u;
+        code |= expand_bits_21(q) << a;
+    }
+    return code;
+}
+
+// ------------------------------------------------------------------------------------------ binary hierarchy
+// Node ids: internal j in [0, n-1), leaf i -> (n-1) + i.  Boxes for all 2n-1 nodes in lo/hi (xyz), with
+//   lo.w = SAH cost of the subtree, hi.w = bits(count | LEAF_MARK if the subtree is collapsed into one leaf slot)
+struct Bvh2 {
+    uint32_t n;
+    const uint64_t *keys;  // sorted Morton codes
+    const uint32_t *order; // sorted position -> input primitive
+    f4 *lo, *hi;           // [2n-1]
+    u2 *child;             // [n-1]
+    u2 *range;             // [n-1]  (left end set by the left child, right end by the right child)
+    uint32_t *flag;        // [n-1]  zero-initialised arrival counters
+    uint32_t *root;        // [1]
+    float ci;              // cost of one binary split relative to one primitive test
+    uint32_t max_leaf;
+};
+
+LCRT_HD bool delta_less(const uint64_t *keys, uint32_t a, uint32_t b) {// delta(a) < delta(b); delta(j) between j and j+1
+    const uint64_t xa = keys[a] ^ keys[a + 1], xb = keys[b] ^ keys[b + 1];
+    if (xa != xb) return xa < xb;
+    return (a ^ (a + 1)) < (b ^ (b + 1));
+}
+
+LCRT_HD float area_of(const f4 lo, const f4 hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    if (!(dx >= 0.f) || !(dy >= 0.f) || !(dz >= 0.f)) return 0.f;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// one thread per leaf (Apetrei 2014): climbs while it is the second child to arrive
+LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
+    const uint32_t n = t.n;
+    uint32_t left = i, right = i, cur = (n - 1) + i;
+    f4 lo = make_f4(leaf_box.lo[0], leaf_box.lo[1], leaf_box.lo[2], 0.f);
+    f4 hi = make_f4(leaf_box.hi[0], leaf_box.hi[1], leaf_box.hi[2], 0.f);
+    float cost = area_of(lo, hi);
+    uint32_t count = 1u, mark = LEAF_MARK;
+    for (;;) {
+        lo.w = cost, hi.w = as_float(count | mark);
+        t.lo[cur] = lo, t.hi[cur] = hi;
+        if (left == 0u && right == n - 1u) {
+            *t.root = cur;
+            return;
+        }
+        uint32_t parent;
+        bool from_left;
+        if (left == 0u || (right != n - 1u && delta_less(t.keys, right, left - 1u))) {
+            parent = right, from_left = true;
+            t.child[parent].x = cur, t.range[parent].x = left;
+        } else {
+            parent = left - 1u, from_left = false;
+            t.child[parent].y = cur, t.range[parent].y = right;
+        }
+        LCRT_FENCE();
+        if (LCRT_ATOMIC_ADD(&t.flag[parent], 1u) == 0u) return;// the sibling will finish this node
+        LCRT_FENCE();
+        // second arrival: merge with the sibling
+        const uint32_t sib = LCRT_VOLATILE_LOAD_U32(from_left ? &t.child[parent].y : &t.child[parent].x);
+        if (from_left) right = LCRT_VOLATILE_LOAD_U32(&t.range[parent].y);
+        else left = LCRT_VOLATILE_LOAD_U32(&t.range[parent].x);
+        const f4 slo = t.lo[sib], shi = t.hi[sib];
+        lo.x = fminf(lo.x, slo.x), lo.y = fminf(lo.y, slo.y), lo.z = fminf(lo.z, slo.z);
+        hi.x = fmaxf(hi.x, shi.x), hi.y = fmaxf(hi.y, shi.y), hi.z = fmaxf(hi.z, shi.z);
+        count += as_uint(shi.w) & ~LEAF_MARK;
+        const float area = area_of(lo, hi);
+        const float c_split = t.ci * area + cost + slo.w;
+        const float c_leaf = area * (float)count;
+        if (count <= t.max_leaf && c_leaf <= c_split) cost = c_leaf, mark = LEAF_MARK;
+        else cost = c_split, mark = 0u;
+        cur = parent;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ BVH8 emission
+struct Bvh8Out {
+    BlobHeader *header;
+    Node8 *nodes;
+    char *prims;
+    uint32_t *parent;     // optional (allow_update): (parent << 3) | slot
+    uint32_t *task;       // [node_capacity] bvh2 node id per wide node, INVALID until scheduled
+    uint32_t *counters;   // [0] nodes allocated, [1] prims allocated, [2] prims finished
+    uint32_t node_capacity;
+};
+
+LCRT_HD void quantize_node(Node8 &nd, const Box &nb, const Box *cb, const bool *valid) {
+    float p[3];
+    uint32_t eb[3];
+    double scale[3];
+    for (int a = 0; a < 3; a++) {
+        const bool ok = nb.lo[a] <= nb.hi[a];// false for empty / NaN bounds
+        p[a] = ok ? nb.lo[a] : 0.f;
+        const double ext = ok ? (double)nb.hi[a] - (double)nb.lo[a] : 0.0;
+        uint32_t e = 0u;
+        if (ext > 0.0) {
+            int ex;
+            // smallest e with 255 * 2^(e-127) >= ext
+            const double m = frexp(ext / 255.0, &ex);// ext/255 = m * 2^ex, m in [0.5, 1)
+            int ee = (m == 0.5) ? ex - 1 : ex;
+            ee += 127;
+            if (ee < 1) ee = 1;
+            if (ee > 254) ee = 254;
+            e = (uint32_t)ee;
+        }
+        eb[a] = e;
+        scale[a] = e ? ldexp(1.0, (int)e - 127) : 0.0;
+    }
+    nd.px = p[0], nd.py = p[1], nd.pz = p[2];
+    nd.ex = (uint8_t)eb[0], nd.ey = (uint8_t)eb[1], nd.ez = (uint8_t)eb[2];
+    uint8_t *qlo[3] = {nd.qlo_x, nd.qlo_y, nd.qlo_z};
+    uint8_t *qhi[3] = {nd.qhi_x, nd.qhi_y, nd.qhi_z};
+    for (int s = 0; s < 8; s++) {
+        for (int a = 0; a < 3; a++) {
+            uint32_t ql = 255u, qh = 0u;// inverted: never hit
+            if (valid[s] && cb[s].lo[a] <= cb[s].hi[a]) {
+                if (scale[a] > 0.0) {
+                    double l = floor(((double)cb[s].lo[a] - (double)p[a]) / scale[a]);
+                    double h = ceil(((double)cb[s].hi[a] - (double)p[a]) / scale[a]);
+                    if (l < 0.0) l = 0.0;
+                    if (l > 255.0) l = 255.0;
+                    if (h < 0.0) h = 0.0;
+                    if (h > 255.0) h = 255.0;
+                    ql = (uint32_t)l, qh = (uint32_t)h;
+                } else {
+                    ql = 0u, qh = 0u;
+                }
+            }
+            qlo[a][s] = (uint8_t)ql, qhi[a][s] = (uint8_t)qh;
+        }
+    }
+}
+
+// collect the sorted positions of the primitives under a leaf-marked subtree (count <= 3)
+LCRT_HD uint32_t gather_leaf(const Bvh2 &t, uint32_t id, uint32_t *out, uint32_t cap) {
+    uint32_t stack[8];
+    int sp = 0;
+    uint32_t k = 0;
+    stack[sp++] = id;
+    while (sp) {
+        const uint32_t c = stack[--sp];
+        if (c >= t.n - 1u) {
+            if (k < cap) out[k++] = c - (t.n - 1u);
+        } else {
+            const u2 ch = t.child[c];
+            stack[sp++] = ch.y, stack[sp++] = ch.x;
+        }
+    }
+    return k;
+}
+
+// Builds wide node `widx` from binary subtree `bid`.  Returns false on capacity overflow.
+template<class Input>
+LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid) {
+    uint32_t cid[8];
+    Box cbox[8];
+    float carea[8];
+    bool cleaf[8];
+    int nc = 0;
+    auto load_child = [&](int k, uint32_t id) {
+        const f4 lo = t.lo[id], hi = t.hi[id];
+        cid[k] = id;
+        cbox[k].lo[0] = lo.x, cbox[k].lo[1] = lo.y, cbox[k].lo[2] = lo.z;
+        cbox[k].hi[0] = hi.x, cbox[k].hi[1] = hi.y, cbox[k].hi[2] = hi.z;
+        carea[k] = area_of(lo, hi);
+        cleaf[k] = (as_uint(hi.w) & LEAF_MARK) != 0u;
+    };
+    {
+        const f4 hi = t.hi[bid];
+        if (as_uint(hi.w) & LEAF_MARK) {
+            load_child(0, bid);
+            nc = 1;
+        } else {
+            const u2 ch = t.child[bid];
+            load_child(0, ch.x), load_child(1, ch.y);
+            nc = 2;
+        }
+    }
+    // greedy surface-area opening until eight children
+    while (nc < 8) {
+        int best = -1;
+        float ba = -1.f;
+        for (int k = 0; k < nc; k++)
+            if (!cleaf[k] && carea[k] > ba) ba = carea[k], best = k;
+        if (best < 0) break;
+        const u2 ch = t.child[cid[best]];
+        load_child(best, ch.x);
+        load_child(nc++, ch.y);
+    }
+    Box nb = box_empty();
+    for (int k = 0; k < nc; k++) box_grow(nb, cbox[k]);
+    // ---- octant-ordered slot assignment (greedy maximum of (centroid - centre) . octant sign)
+    float cx = 0.5f * (nb.lo[0] + nb.hi[0]), cy = 0.5f * (nb.lo[1] + nb.hi[1]), cz = 0.5f * (nb.lo[2] + nb.hi[2]);
+    if (!(cx == cx)) cx = 0.f;
+    if (!(cy == cy)) cy = 0.f;
+    if (!(cz == cz)) cz = 0.f;
+    int slot_of[8], child_at[8];
+    for (int k = 0; k < 8; k++) slot_of[k] = -1, child_at[k] = -1;
+    for (int round = 0; round < nc; round++) {
+        float bestv = -INFINITY;
+        int bk = -1, bs = -1;
+        for (int k = 0; k < nc; k++) {
+            if (slot_of[k] >= 0) continue;
+            float ddx = 0.5f * (cbox[k].lo[0] + cbox[k].hi[0]) - cx, ddy = 0.5f * (cbox[k].lo[1] + cbox[k].hi[1]) - cy,
+                  ddz = 0.5f * (cbox[k].lo[2] + cbox[k].hi[2]) - cz;
+            if (!(ddx == ddx)) ddx = 0.f;
+            if (!(ddy == ddy)) ddy = 0.f;
+            if (!(ddz == ddz)) ddz = 0.f;
+            for (int s = 0; s < 8; s++) {
+                if (child_at[s] >= 0) continue;
+                const float v = ((s & 1) ? ddx : -ddx) + ((s & 2) ? ddy : -ddy) + ((s & 4) ? ddz : -ddz);
+                if (v > bestv || bk < 0) bestv = v, bk = k, bs = s;
+            }
+        }
+        slot_of[bk] = bs, child_at[bs] = bk;
+    }
+    // ---- allocate children / primitive records
+    uint32_t n_int = 0, n_prims = 0;
+    for (int k = 0; k < nc; k++) {
+        if (cleaf[k]) n_prims += as_uint(t.hi[cid[k]].w) & ~LEAF_MARK;
+        else n_int++;
+    }
+    const uint32_t child_base = n_int ? LCRT_ATOMIC_ADD(&o.counters[0], n_int) : 0u;
+    const uint32_t prim_base = n_prims ? LCRT_ATOMIC_ADD(&o.counters[1], n_prims) : 0u;
+    if (n_int && child_base + n_int > o.node_capacity) {
+        o.header->error = 1u;
+        return false;
+    }
+    Node8 nd;
+    nd.imask = 0;
+    nd.child_base = child_base, nd.prim_base = prim_base;
+    Box sbox[8];
+    bool svalid[8];
+    uint32_t ci = 0, po = 0;
+    for (int s = 0; s < 8; s++) {
+        const int k = child_at[s];
+        svalid[s] = k >= 0;
+        nd.meta[s] = 0;
+        if (k < 0) continue;
+        sbox[s] = cbox[k];
+        if (!cleaf[k]) {
+            const uint32_t w = child_base + ci++;
+            nd.imask |= (uint8_t)(1u << s);
+            nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
+            if (o.parent) o.parent[w] = (widx << 3) | (uint32_t)s;
+            o.task[w] = cid[k];
+        } else {
+            uint32_t pos[4];
+            const uint32_t cnt = gather_leaf(t, cid[k], pos, 3u);
+            for (uint32_t q = 0; q < cnt; q++)
+                in.write(o.prims + (uint64_t)(prim_base + po + q) * Input::rec_bytes, t.order[pos[q]]);
+            const uint32_t unary = cnt == 1u ? 1u : cnt == 2u ? 3u : 7u;
+            nd.meta[s] = (uint8_t)((unary << 5) | po);
+            po += cnt;
+        }
+    }
+    quantize_node(nd, nb, sbox, svalid);
+    copy_vec16(&o.nodes[widx], &nd, 5);
+    if (widx == 0u) {
+        for (int a = 0; a < 3; a++) o.header->lo[a] = nb.lo[a], o.header->hi[a] = nb.hi[a];
+        if (o.parent) o.parent[0] = INVALID_U32;
+    }
+    LCRT_FENCE();// tasks, parents and records are visible before the completion counter moves
+    if (n_prims) LCRT_ATOMIC_ADD(&o.counters[2], n_prims);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ refit
+struct RefitCtx {
+    BlobHeader *header;
+    Node8 *nodes;
+    char *prims;
+    const uint32_t *parent;
+    f4 *box_lo, *box_hi;  // [node_count] exact boxes (temp)
+    uint32_t *arrived;    // [node_count] zero-initialised (temp)
+};
+
+LCRT_HD Box record_box_tri(const char *rec) {
+    const f4 *r = reinterpret_cast<const f4 *>(rec);
+    Box b = box_empty();
+    box_grow(b, r[0].x, r[0].y, r[0].z), box_grow(b, r[1].x, r[1].y, r[1].z), box_grow(b, r[2].x, r[2].y, r[2].z);
+    return b;
+}
+
+// Recompute one node from its (already rewritten) primitive records and its internal children's exact boxes.
+template<class Input>
+LCRT_HD void refit_node(const RefitCtx &c, const Input &in, uint32_t widx) {
+    Node8 nd = c.nodes[widx];
+    Box sbox[8];
+    bool svalid[8];
+    Box nb = box_empty();
+    uint32_t ci = 0;
+    for (int s = 0; s < 8; s++) {
+        const uint32_t meta = nd.meta[s];
+        svalid[s] = meta != 0u;
+        if (!meta) continue;
+        Box b = box_empty();
+        if (nd.imask & (1u << s)) {
+            const uint32_t w = nd.child_base + ci++;
+            const f4 lo = c.box_lo[w], hi = c.box_hi[w];
+            b.lo[0] = lo.x, b.lo[1] = lo.y, b.lo[2] = lo.z, b.hi[0] = hi.x, b.hi[1] = hi.y, b.hi[2] = hi.z;
+        } else {
+            const uint32_t cnt = popc(meta >> 5), off = meta & 31u;
+            for (uint32_t q = 0; q < cnt; q++) {
+                const char *rec = c.prims + (uint64_t)(nd.prim_base + off + q) * Input::rec_bytes;
+                box_grow(b, in.box(Input::record_prim(rec)));
+            }
+        }
+        sbox[s] = b;
+        box_grow(nb, b);
+    }
+    quantize_node(nd, nb, sbox, svalid);
+    copy_vec16(&c.nodes[widx], &nd, 5);
+    c.box_lo[widx] = make_f4(nb.lo[0], nb.lo[1], nb.lo[2], 0.f);
+    c.box_hi[widx] = make_f4(nb.hi[0], nb.hi[1], nb.hi[2], 0.f);
+    if (widx == 0u)
+        for (int a = 0; a < 3; a++) c.header->lo[a] = nb.lo[a], c.header->hi[a] = nb.hi[a];
+}
+
+// one thread per wide node: nodes without internal children start, the last child to arrive refits the parent
+template<class Input>
+LCRT_HD void refit_climb(const RefitCtx &c, const Input &in, uint32_t widx) {
+    if (c.nodes[widx].imask != 0) return;
+    uint32_t cur = widx;
+    for (;;) {
+        refit_node(c, in, cur);
+        if (cur == 0u) return;
+        const uint32_t p = c.parent[cur] >> 3;
+        LCRT_FENCE();
+        const uint32_t need = (uint32_t)popc(c.nodes[p].imask);
+        if (LCRT_ATOMIC_ADD(&c.arrived[p], 1u) + 1u < need) return;
+        LCRT_FENCE();
+        cur = p;
+    }
+}
+
+}// namespace lcrt

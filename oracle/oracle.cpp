@@ -412,7 +412,8 @@ struct Tracer {
                 if (!tri_hit(lo, ld, g.verts[g.tris[3 * p]], g.verts[g.tris[3 * p + 1]], g.verts[g.tris[3 * p + 2]], 0.0, t, u, v))
                     return true;
                 if (t < tmin || t > r.tmax) return true;// Embree: tnear <= t <= tfar
-                if (!have || t < res.t) {
+                // exact ties resolve towards the lower (inst, prim) so the answer is independent of traversal order
+                if (!have || t < res.t || (t == res.t && (ii < res.inst || (ii == res.inst && p < res.prim)))) {
                     if (have) res.t2 = res.t;
                     res.t = t, res.u = u, res.v = v, res.inst = ii, res.prim = p, have = true;
                 } else if (t < res.t2) {

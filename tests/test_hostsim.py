@@ -1,0 +1,163 @@
+"""CPU execution of the device headers (builder + BVH8 traversal) against the oracle.
+
+These tests validate the *algorithms* the CUDA kernels run (same source: luisacompute_b200/csrc/lcrt_*.h compiled by
+g++); the GPU parity tests proper are in test_gpu_*.py (-m gpu).
+"""
+import numpy as np
+import pytest
+
+from luisacompute_b200 import scenes as S
+from tests.hostsim import hostsim_py as H
+
+
+def _pair(oracle, meshes, affines, blas_index=None, masks=None, opaque=None, user_ids=None, flags=0):
+    """Build the same scene in the oracle and in the host simulation."""
+    blas_index = list(range(len(affines))) if blas_index is None else blas_index
+    om, sm = [], []
+    for g in meshes:
+        if isinstance(g, tuple):
+            om.append(oracle.OracleMesh(*g)), sm.append(H.SimMesh(*g, flags=flags))
+        else:
+            om.append(oracle.OracleProcedural(g)), sm.append(H.SimProcedural(g, flags=flags))
+    oa, sa = oracle.OracleAccel(), H.SimAccel(flags=flags)
+    oa._keep, sa._keep = om, sm
+    n = len(affines)
+    assert oa.update(n, S.make_mods([om[b].handle for b in blas_index], affines, masks, opaque, user_ids)) == 0
+    sa.update(n, S.make_mods([sm[b].handle for b in blas_index], affines, masks, opaque, user_ids))
+    return oa, sa
+
+
+def _check_closest(oracle, oa, sa, rays, mask=0xFF, allow_soft=0):
+    got = sa.trace_closest(rays, mask)
+    res = oracle.compare_closest(oa, rays, got, mask)
+    assert res["id_mismatch"] == 0, res
+    assert res["t_bad"] == 0 and res["bary_bad"] == 0, res
+    assert res["tie"] + res["grazing"] <= allow_soft, res
+    return res
+
+
+def test_structure_and_c1(oracle):
+    verts, tris, xf = S.test_rtx_scene()
+    oa, sa = _pair(oracle, [(verts, tris)], xf, blas_index=[0, 0])
+    assert sa._keep[0].validate()[0] == 0 and sa.validate()[0] == 0
+    rays = S.test_rtx_rays(96, 96)
+    res = _check_closest(oracle, oa, sa, rays)
+    assert res["exact"] == len(rays)
+    assert np.array_equal(sa.trace_any(rays) != 0, oa.trace_any(rays) != 0)
+
+
+@pytest.mark.parametrize("level", [0, 3, 5])
+def test_icosphere_identity_exact(oracle, level):
+    verts, tris = S.icosphere(level)
+    oa, sa = _pair(oracle, [(verts, tris)], [S.affine_identity()])
+    rc, st = sa._keep[0].validate()
+    assert rc == 0
+    prim = S.pinhole_rays(96, 96)
+    res = _check_closest(oracle, oa, sa, prim)
+    assert res["exact"] == len(prim)          # identity transform: decisions are made in double on identical inputs
+    hits = sa.trace_closest(prim)
+    b = S.bounce_rays(prim, hits, verts, tris, 96, 96)
+    res = _check_closest(oracle, oa, sa, b)
+    assert res["exact"] == len(b)
+    assert np.array_equal(sa.trace_any(b) != 0, oa.trace_any(b) != 0)
+
+
+def test_soup_instances_masks(oracle):
+    verts, tris = S.triangle_soup(5000, seed=3, s=0.05)
+    rng = np.random.default_rng(5)
+    xf = [S.affine_from_4x4(S.mat_translation(*rng.uniform(-0.5, 0.5, 3)) @ S.mat_rotation(rng.normal(size=3), rng.uniform(0, 6)) @ S.mat_scaling(rng.uniform(0.5, 1.5)))
+          for _ in range(9)]
+    masks = [1 << (i & 7) for i in range(9)]
+    oa, sa = _pair(oracle, [(verts, tris)], xf, blas_index=[0] * 9, masks=masks)
+    assert sa.validate()[0] == 0
+    rays = S.uniform_rays(6000, seed=77)
+    for mask in (0xFF, 0x55, 0x01):
+        _check_closest(oracle, oa, sa, rays, mask, allow_soft=12)
+        a, b = sa.trace_any(rays, mask) != 0, oa.trace_any(rays, mask) != 0
+        assert np.count_nonzero(a != b) <= 2
+    # per-ray masks
+    pm = (1 << (np.arange(len(rays)) % 8)).astype(np.uint32)
+    _check_closest(oracle, oa, sa, rays, pm, allow_soft=12)
+
+
+def test_degenerate_inputs(oracle):
+    # duplicate / zero-area triangles, a single triangle, an empty mesh instance next to a real one
+    verts = np.zeros((6, 4), dtype=np.float32)
+    verts[:, :3] = [(0, 0, 0), (1, 0, 0), (0, 1, 0), (0, 0, 0), (0, 0, 0), (2, 2, 2)]
+    tris = np.array([[0, 1, 2], [0, 1, 2], [3, 4, 5], [3, 3, 3], [0, 1, 2]], dtype=np.uint32)
+    oa, sa = _pair(oracle, [(verts, tris)], [S.affine_identity()])
+    assert sa._keep[0].validate()[0] == 0
+    rays = np.zeros(3, dtype=S.RAY_DTYPE)
+    rays["o"] = [(0.2, 0.2, 1), (0.9, 0.9, 1), (0.2, 0.2, -1)]
+    rays["d"] = [(0, 0, -1), (0, 0, -1), (0, 0, 1)]
+    rays["tmax"] = S.FLT_MAX
+    got = sa.trace_closest(rays)
+    exp = oa.trace_closest(rays)[0]
+    assert list(got["inst"]) == list(exp["inst"]) == [0, 0xFFFFFFFF, 0]
+    assert list(got["prim"][[0, 2]]) == [0, 0]      # exact ties resolve to the lowest primitive id on both sides
+    # tmin / tmax window and empty interval
+    rays["tmin"], rays["tmax"] = 0.5, 0.9
+    assert np.all(sa.trace_closest(rays)["inst"] == 0xFFFFFFFF)
+    rays["tmin"], rays["tmax"] = 0.5, 1.0
+    assert list(sa.trace_closest(rays)["inst"]) == [0, 0xFFFFFFFF, 0]      # t == tmax is a hit (tnear <= t <= tfar)
+    rays["tmin"], rays["tmax"] = 2.0, 1.0
+    assert np.all(sa.trace_closest(rays)["inst"] == 0xFFFFFFFF)
+    # empty mesh
+    em = H.SimMesh(np.zeros((0, 4), np.float32), np.zeros((0, 3), np.uint32))
+    assert em.validate()[0] == 0
+    sa2 = H.SimAccel()
+    sa2.update(2, S.make_mods([em.handle, sa._keep[0].handle], [S.affine_identity()] * 2))
+    rays["tmin"], rays["tmax"] = 0.0, S.FLT_MAX
+    assert list(sa2.trace_closest(rays)["inst"]) == [1, 0xFFFFFFFF, 1]
+
+
+def test_refit_and_update(oracle):
+    verts, tris = S.icosphere(3)
+    sm = H.SimMesh(verts, tris, flags=H.BUILD_ALLOW_UPDATE)
+    sa = H.SimAccel(flags=H.BUILD_ALLOW_UPDATE)
+    xf = [S.affine_identity(), S.affine_from_4x4(S.mat_translation(2.5, 0, 0))]
+    sa.update(2, S.make_mods([sm.handle] * 2, xf))
+    # deform the mesh, refit the BLAS, move an instance, refit the TLAS
+    v2 = verts.copy()
+    v2[:, :3] *= (1.0 + 0.3 * np.sin(5 * verts[:, 0:1])).astype(np.float32)
+    sm.refit(v2)
+    assert sm.validate()[0] == 0
+    m = np.zeros(1, dtype=S.MOD_DTYPE)
+    m["index"], m["flags"] = 1, S.MOD_TRANSFORM
+    m["affine"][0] = S.affine_from_4x4(S.mat_translation(-2.5, 0.5, 0) @ S.mat_rotation((0, 1, 0), 0.7))
+    sa.update(2, m, refit=True)
+    assert sa.validate()[0] == 0
+    om = oracle.OracleMesh(v2, tris)
+    oa = oracle.OracleAccel()
+    oa._keep.append(om)
+    assert oa.update(2, S.make_mods([om.handle] * 2, [xf[0], m["affine"][0]])) == 0
+    rays = S.pinhole_rays(80, 80, pos=(0, 0, 7), vfov_deg=50)
+    _check_closest(oracle, oa, sa, rays, allow_soft=6)
+
+
+def test_ray_query(oracle):
+    aabbs = S.sphere_aabbs(64, radius=0.1)
+    verts, tris, _ = S.test_rtx_scene()
+    cv, ct = S.icosphere(2)
+    xf = [S.affine_identity(), S.affine_from_4x4(S.mat_scaling(3.0)), S.affine_from_4x4(S.mat_translation(0, 0, -2) @ S.mat_scaling(0.7))]
+    oa, sa = _pair(oracle, [aabbs, (verts, tris), (cv, ct)], xf, opaque=[False, False, True])
+    assert sa._keep[0].validate()[0] == 0
+    rays = S.pinhole_rays(96, 96, pos=(0, 0, 4), vfov_deg=35)
+    for tri_prog in (0, 1, 2):
+        e = oa.query(rays, 0xFF, False, tri_prog, 0)
+        g = sa.query(rays, 0xFF, False, tri_prog, 0)
+        assert np.array_equal(e["hit_type"], g["hit_type"])
+        assert np.array_equal(e["inst"], g["inst"])
+        hit = e["hit_type"] != 0
+        assert np.array_equal(e["prim"][hit], g["prim"][hit])
+        np.testing.assert_allclose(g["t"][hit], e["t"][hit], rtol=1e-5)
+        np.testing.assert_allclose(g["bary"][hit], e["bary"][hit], atol=1e-4)
+    # query_any: hit / miss only (D5)
+    e = oa.query(rays, 0xFF, True, 0, 0)
+    g = sa.query(rays, 0xFF, True, 0, 0)
+    assert np.array_equal(e["hit_type"] != 0, g["hit_type"] != 0)
+    # intersect() ignores procedural primitives
+    got = sa.trace_closest(rays)
+    assert not np.any(got["inst"] == 0)
+    res = oracle.compare_closest(oa, rays, got)
+    assert res["id_mismatch"] == 0
