@@ -1,0 +1,114 @@
+/* lcb200_device.h — flat C API of the host-side device layer (C++ implementation in luisacompute_b200/host/).
+ *
+ * Mirrors, for the ray-tracing path only, the reference's backend interface and its CUDA implementation
+ * (paths relative to /root/reference):
+ *
+ *   lcbDeviceCreate / Destroy          <- extern "C" create / destroy      src/backends/cuda/cuda_device.cpp:1192-1211
+ *   lcbCreateMesh / DestroyMesh        <- DeviceInterface::create_mesh / destroy_mesh          cuda_device.cpp:909-921
+ *   lcbCreateProceduralPrimitive / ... <- create_procedural_primitive / destroy_...           cuda_device.cpp:939-951
+ *   lcbCreateAccel / DestroyAccel      <- create_accel / destroy_accel                         cuda_device.cpp:969-981
+ *   lcbMeshBuild                       <- CUDACommandEncoder::visit(MeshBuildCommand*) -> CUDAMesh::build   cuda_mesh.cpp:31-69
+ *   lcbProceduralPrimitiveBuild        <- visit(ProceduralPrimitiveBuildCommand*) -> CUDAProceduralPrimitive::build
+ *                                                                                  cuda_procedural_primitive.cpp:26-55
+ *   lcbAccelBuild                      <- visit(AccelBuildCommand*) -> CUDAAccel::build        cuda_accel.cpp:152-318
+ *   lcbAccelGetBinding                 <- CUDAAccel::binding()                                 cuda_accel.h:29-32
+ *   lcbTraceClosest / Any / Query      <- a ShaderDispatchCommand of a kernel that only calls accel.intersect / ...
+ *
+ * Command structs carry the same fields as include/luisa/runtime/rhi/command.h:407-444 (MeshBuildCommand),
+ * :489-510 (ProceduralPrimitiveBuildCommand), :531-616 (AccelBuildCommand); a "buffer handle" is a device address.
+ * Like the reference, nothing here returns errors for misuse in normal operation: failures are logged to stderr
+ * and reported as a negative code (the plugin shim aborts on them, as LUISA_ERROR_WITH_LOCATION does).
+ * All work is stream-ordered; no call synchronises the host except lcbSynchronize and the *Info getters.
+ */
+#ifndef LCB200_DEVICE_H
+#define LCB200_DEVICE_H
+
+#include <stdint.h>
+
+#include "lcb200_rt.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lcbDevice lcbDevice;
+
+/* AccelOption, include/luisa/runtime/rhi/resource.h:94-126 */
+typedef struct lcbAccelOption {
+    uint32_t hint;            /* 0 FAST_TRACE, 1 FAST_BUILD */
+    uint32_t allow_compaction;/* default true in the reference; accepted, see DESIGN.md (no host stall) */
+    uint32_t allow_update;    /* default false */
+} lcbAccelOption;
+
+enum { LCB_BUILD_PREFER_UPDATE = 0, LCB_BUILD_FORCE_BUILD = 1 }; /* AccelBuildRequest, command.h:402-405 */
+
+typedef struct lcbMeshBuildCommand {
+    uint64_t handle;
+    uint32_t request;
+    uint64_t vertex_buffer, vertex_buffer_offset, vertex_buffer_size, vertex_stride;
+    uint64_t triangle_buffer, triangle_buffer_offset, triangle_buffer_size;
+} lcbMeshBuildCommand;
+
+typedef struct lcbProceduralPrimitiveBuildCommand {
+    uint64_t handle;
+    uint32_t request;
+    uint64_t aabb_buffer, aabb_buffer_offset, aabb_buffer_size;
+} lcbProceduralPrimitiveBuildCommand;
+
+typedef struct lcbAccelBuildCommand {
+    uint64_t handle;
+    uint32_t instance_count;
+    uint32_t request;
+    uint32_t update_instance_buffer_only;
+    uint32_t modification_count;
+    const void *modifications; /* host array of 80-byte Modification records; `primitive` holds mesh / procedural handles */
+} lcbAccelBuildCommand;
+
+typedef struct lcbAccelBinding {
+    uint64_t handle;    /* device address of the TLAS blob */
+    uint64_t instances; /* device address of the 80-byte instance array */
+} lcbAccelBinding;
+
+LCRT_API lcbDevice *lcbDeviceCreate(int device_index);
+LCRT_API void lcbDeviceDestroy(lcbDevice *device);
+LCRT_API const char *lcbBackendName(void);
+
+LCRT_API uint64_t lcbCreateMesh(lcbDevice *device, const lcbAccelOption *option);
+LCRT_API void lcbDestroyMesh(lcbDevice *device, uint64_t handle);
+LCRT_API uint64_t lcbCreateProceduralPrimitive(lcbDevice *device, const lcbAccelOption *option);
+LCRT_API void lcbDestroyProceduralPrimitive(lcbDevice *device, uint64_t handle);
+LCRT_API uint64_t lcbCreateAccel(lcbDevice *device, const lcbAccelOption *option);
+LCRT_API void lcbDestroyAccel(lcbDevice *device, uint64_t handle);
+
+LCRT_API int lcbMeshBuild(lcbDevice *device, lcrtStream stream, const lcbMeshBuildCommand *command);
+LCRT_API int lcbProceduralPrimitiveBuild(lcbDevice *device, lcrtStream stream, const lcbProceduralPrimitiveBuildCommand *command);
+LCRT_API int lcbAccelBuild(lcbDevice *device, lcrtStream stream, const lcbAccelBuildCommand *command);
+LCRT_API int lcbAccelGetBinding(lcbDevice *device, uint64_t accel, lcbAccelBinding *out);
+
+/* what the last build of a primitive / accel did: 0 nothing yet, 1 full build, 2 refit (update) */
+LCRT_API int lcbLastBuildKind(lcbDevice *device, uint64_t handle);
+/* native handle (device address of the blob) of a mesh / procedural primitive / accel */
+LCRT_API uint64_t lcbNativeHandle(lcbDevice *device, uint64_t handle);
+LCRT_API int lcbBlobInfo(lcbDevice *device, lcrtStream stream, uint64_t handle, lcrtBlobInfo *out);
+
+LCRT_API int lcbTraceClosest(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count,
+                             const uint32_t *masks, uint32_t mask, void *hits, uint64_t *counters);
+LCRT_API int lcbTraceAny(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count,
+                         const uint32_t *masks, uint32_t mask, uint32_t *occluded, uint64_t *counters);
+LCRT_API int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                      uint32_t mask, int terminate_on_first, uint32_t tri_program, uint32_t proc_program, void *hits);
+
+/* Host-buffer convenience (the end-to-end path bench.py times as `e2e`): rays in pinned host memory -> chunked,
+ * double-buffered H2D copy / trace / D2H copy on internal streams -> hits in pinned host memory.  Synchronous. */
+LCRT_API int lcbTraceClosestHost(lcbDevice *device, uint64_t accel, const void *host_rays, uint64_t ray_count, uint32_t mask,
+                                 void *host_hits, uint64_t chunk_rays);
+
+LCRT_API int lcbSynchronize(lcbDevice *device, lcrtStream stream);
+/* BufferDownloadCommand / BufferUploadCommand analogues for raw device addresses (synchronous) */
+LCRT_API int lcbDownload(lcbDevice *device, lcrtStream stream, uint64_t device_address, void *host, uint64_t bytes);
+LCRT_API int lcbUpload(lcbDevice *device, lcrtStream stream, uint64_t device_address, const void *host, uint64_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LCB200_DEVICE_H */

@@ -13,6 +13,8 @@ namespace lcrt {
 #define LCRT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define LCRT_FENCE() __threadfence()
 #define LCRT_VOLATILE_LOAD_U32(p) (*reinterpret_cast<const volatile uint32_t *>(p))
+// data produced by other SMs inside the same kernel must not be served from this SM's (non-coherent) L1
+#define LCRT_LOAD_CG_F4(p) __ldcg(reinterpret_cast<const float4 *>(p))
 #else
 inline uint32_t host_atomic_add(uint32_t *p, uint32_t v) {
     uint32_t o = *p;
@@ -22,6 +24,7 @@ inline uint32_t host_atomic_add(uint32_t *p, uint32_t v) {
 #define LCRT_ATOMIC_ADD(p, v) ::lcrt::host_atomic_add((p), (v))
 #define LCRT_FENCE() ((void)0)
 #define LCRT_VOLATILE_LOAD_U32(p) (*(p))
+#define LCRT_LOAD_CG_F4(p) (*(p))
 #endif
 
 constexpr uint32_t INVALID_U32 = 0xffffffffu;
@@ -165,19 +168,32 @@ LCRT_HD uint64_t expand_bits_21(uint64_t v) {// spread the low 21 bits to every 
     return v;
 }
 
-// 63-bit Morton code of the box centre relative to the centroid bounds [clo, chi]
-LCRT_HD uint64_t morton63(const Box &b, const float clo[3], const float inv_ext[3]) {
+// Morton code (3 x `bits`, bits <= 21) of the box centre relative to the centroid bounds [clo, chi]
+LCRT_HD uint64_t morton63(const Box &b, const float clo[3], const float inv_ext[3], uint32_t bits) {
     uint64_t code = 0;
+    const float scale = (float)(1u << bits);
+    const uint32_t qmax = (1u << bits) - 1u;
     for (int a = 0; a < 3; a++) {
         const float c = 0.5f * (b.lo[a] + b.hi[a]);
         float f = (c - clo[a]) * inv_ext[a];// [0, 1]
         if (!(f >= 0.f)) f = 0.f;           // also catches NaN (empty boxes)
         if (f > 1.f) f = 1.f;
-        uint32_t q = (uint32_t)(f * 2097152.0f);
-        if (q > 2097151u) q = 2097151u;
+        uint32_t q = (uint32_t)(f * scale);
+        if (q > qmax) q = qmax;
         code |= expand_bits_21(q) << a;
     }
     return code;
+}
+
+// Bits per axis: enough to resolve 256 cells per primitive of a uniform distribution, at most 21.  The number of
+// 8-bit radix passes follows: ceil(3 * bits / 8).
+LCRT_HD uint32_t morton_bits_for(uint32_t n) {
+    uint32_t lg = 0;
+    while ((1ull << lg) < (uint64_t)n) lg++;
+    uint32_t b = (lg + 2u) / 3u + 8u;
+    if (b < 10u) b = 10u;
+    if (b > 21u) b = 21u;
+    return b;
 }
 
 // ------------------------------------------------------------------------------------------ binary hierarchy
@@ -239,7 +255,7 @@ LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
         const uint32_t sib = LCRT_VOLATILE_LOAD_U32(from_left ? &t.child[parent].y : &t.child[parent].x);
         if (from_left) right = LCRT_VOLATILE_LOAD_U32(&t.range[parent].y);
         else left = LCRT_VOLATILE_LOAD_U32(&t.range[parent].x);
-        const f4 slo = t.lo[sib], shi = t.hi[sib];
+        const f4 slo = LCRT_LOAD_CG_F4(&t.lo[sib]), shi = LCRT_LOAD_CG_F4(&t.hi[sib]);
         lo.x = fminf(lo.x, slo.x), lo.y = fminf(lo.y, slo.y), lo.z = fminf(lo.z, slo.z);
         hi.x = fmaxf(hi.x, shi.x), hi.y = fmaxf(hi.y, shi.y), hi.z = fmaxf(hi.z, shi.z);
         count += as_uint(shi.w) & ~LEAF_MARK;
@@ -476,7 +492,7 @@ LCRT_HD void refit_node(const RefitCtx &c, const Input &in, uint32_t widx) {
         Box b = box_empty();
         if (nd.imask & (1u << s)) {
             const uint32_t w = nd.child_base + ci++;
-            const f4 lo = c.box_lo[w], hi = c.box_hi[w];
+            const f4 lo = LCRT_LOAD_CG_F4(&c.box_lo[w]), hi = LCRT_LOAD_CG_F4(&c.box_hi[w]);
             b.lo[0] = lo.x, b.lo[1] = lo.y, b.lo[2] = lo.z, b.hi[0] = hi.x, b.hi[1] = hi.y, b.hi[2] = hi.z;
         } else {
             const uint32_t cnt = popc(meta >> 5), off = meta & 31u;

@@ -1,0 +1,672 @@
+// lcrt_kernels.cu — sm_100a kernels and the C-ABI (include/lcb200_rt.h) of liblcb200_rt.so.
+//
+// Build pipeline (all stream-ordered, zero host synchronisation — the reference stalls the host once per compacted
+// build, src/backends/cuda/cuda_primitive.cpp:74, cuda_accel.cpp:90):
+//   k_build_init -> k_centroid_bounds -> k_morton -> radix sort (lcrt_sort.cuh) -> k_climb (agglomerative LBVH + SAH
+//   leaf marking) -> k_collapse (persistent work-queue kernel: BVH2 -> compressed BVH8 + primitive records)
+//   -> k_build_finalize.
+// Trace: persistent-thread kernels (one resident grid, warp-cooperative ray fetch with __ballot_sync / __shfl_sync
+// compaction of idle lanes, short stack in shared memory with local-memory overflow).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+
+#include "../../include/lcb200_rt.h"
+#include "lcrt_accel.h"
+#include "lcrt_build.h"
+#include "lcrt_layout.h"
+#include "lcrt_query_programs.h"
+#include "lcrt_sort.cuh"
+#include "lcrt_traverse.h"
+
+namespace lcrt {
+
+static_assert(SORT_TILE == SORT_TILE_KEYS, "lcrt_layout.h and lcrt_sort.cuh disagree on the sort tile");
+
+// =====================================================================================================================
+// build kernels
+// =====================================================================================================================
+enum SmallSlots : uint32_t { SM_CMIN = 0, SM_CMAX = 3, SM_ROOT = 6, SM_ABORT = 7, SM_COUNTERS = 8 /* nodes, prims, done */ };
+
+__global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t flags, BlobLayout L, uint32_t *small) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        BlobHeader hd;
+        memset(&hd, 0, sizeof(hd));
+        hd.magic = BLOB_MAGIC, hd.kind = kind, hd.prim_count = n, hd.node_capacity = L.node_capacity;
+        hd.flags = flags, hd.prim_stride = L.prim_stride;
+        hd.nodes_offset = L.nodes_offset, hd.prims_offset = L.prims_offset, hd.parent_offset = L.parent_offset, hd.total_bytes = L.total_bytes;
+        for (int a = 0; a < 3; a++) hd.lo[a] = INFINITY, hd.hi[a] = -INFINITY;
+        *h = hd;
+        small[SM_CMIN + 0] = small[SM_CMIN + 1] = small[SM_CMIN + 2] = 0xffffffffu;
+        small[SM_CMAX + 0] = small[SM_CMAX + 1] = small[SM_CMAX + 2] = 0u;
+        small[SM_ROOT] = INVALID_U32, small[SM_ABORT] = 0u;
+        small[SM_COUNTERS + 0] = 1u, small[SM_COUNTERS + 1] = 0u, small[SM_COUNTERS + 2] = 0u;
+        if (n == 0u) {
+            // an empty structure: one node with no children; nothing can be hit
+            Node8 nd;
+            memset(&nd, 0, sizeof(nd));
+            Box nb = box_empty();
+            Box sb[8];
+            bool sv[8] = {false, false, false, false, false, false, false, false};
+            for (int s = 0; s < 8; s++) sb[s] = nb;
+            quantize_node(nd, nb, sb, sv);
+            Node8 *nodes = reinterpret_cast<Node8 *>(reinterpret_cast<char *>(h) + L.nodes_offset);
+            copy_vec16(&nodes[0], &nd, 5);
+            if (L.parent_offset) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(h) + L.parent_offset) = INVALID_U32;
+            h->node_count = 1u, h->built = 1u;
+        }
+    }
+}
+
+template<class Input>
+__global__ void __launch_bounds__(256) k_centroid_bounds(Input in, uint32_t *small) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += gridDim.x * blockDim.x) {
+        const Box b = in.box(i);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float c = 0.5f * (b.lo[a] + b.hi[a]);
+            if (c == c) lo[a] = fminf(lo[a], c), hi[a] = fmaxf(hi[a], c);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (lo[a] <= hi[a]) {
+                atomicMin(&small[SM_CMIN + a], float_to_ordered(lo[a]));
+                atomicMax(&small[SM_CMAX + a], float_to_ordered(hi[a]));
+            }
+        }
+    }
+}
+
+template<class Input>
+__global__ void __launch_bounds__(256) k_morton(Input in, const uint32_t *__restrict__ small, uint64_t *__restrict__ keys,
+                                                uint32_t *__restrict__ vals, uint32_t bits) {
+    float clo[3], inv_ext[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const uint32_t ulo = small[SM_CMIN + a], uhi = small[SM_CMAX + a];
+        clo[a] = ordered_to_float(ulo);
+        const float ext = ordered_to_float(uhi) - clo[a];
+        inv_ext[a] = ext > 0.f ? 1.0f / ext : 0.f;
+        if (ulo == 0xffffffffu) clo[a] = 0.f, inv_ext[a] = 0.f;
+    }
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < in.n) {
+        keys[i] = morton63(in.box(i), clo, inv_ext, bits);
+        vals[i] = i;
+    }
+}
+
+template<class Input>
+__global__ void __launch_bounds__(256) k_climb(Bvh2 t, Input in) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < t.n) lbvh_climb(t, i, in.box(t.order[i]));
+}
+
+// Persistent work queue: wide node w is built from binary subtree task[w]; children are appended with atomicAdd and
+// their tasks published before the completion counter moves.  The grid never exceeds what is co-resident, so a
+// polling thread can not starve the thread that will publish its task.
+template<class Input>
+__global__ void __launch_bounds__(128) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t polls = 0;
+    while (w < o.node_capacity) {
+        uint32_t bid = (w == 0u) ? *t.root : LCRT_VOLATILE_LOAD_U32(&o.task[w]);
+        if (bid == INVALID_U32) {
+            if (LCRT_VOLATILE_LOAD_U32(&o.counters[2]) >= t.n || LCRT_VOLATILE_LOAD_U32(abort_flag) != 0u) {
+                bid = LCRT_VOLATILE_LOAD_U32(&o.task[w]);// published before the counter moved?
+                if (bid == INVALID_U32) break;
+            } else {
+                if (++polls > (1u << 24)) {// safety net: never hang the device
+                    atomicExch(abort_flag, 2u);
+                    break;
+                }
+                __nanosleep(64);
+                continue;
+            }
+        }
+        if (!collapse_node(t, o, in, w, bid)) {
+            atomicExch(abort_flag, 1u);
+            break;
+        }
+        w += stride;
+    }
+}
+
+__global__ void k_build_finalize(BlobHeader *h, const uint32_t *small, uint32_t n) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        h->node_count = small[SM_COUNTERS + 0];
+        h->prim_written = small[SM_COUNTERS + 1];
+        const bool ok = small[SM_ABORT] == 0u && small[SM_COUNTERS + 2] == n && small[SM_COUNTERS + 0] <= h->node_capacity;
+        h->error = ok ? 0u : (small[SM_ABORT] ? small[SM_ABORT] : 3u);
+        h->built = ok ? 1u : 0u;
+    }
+}
+
+// ---- refit
+// A blob that was not built with ALLOW_UPDATE (no parent array), is unbuilt, or has another primitive count is left
+// untouched and flagged (error = 4) instead of being corrupted.
+__device__ __forceinline__ bool refit_allowed(const BlobHeader *h, uint32_t n) {
+    return h->magic == BLOB_MAGIC && h->built && h->parent_offset != 0ull && h->prim_count == n;
+}
+
+template<class Input>
+__global__ void __launch_bounds__(256) k_refit_records(Input in, BlobHeader *h, char *prims) {
+    if (!refit_allowed(h, in.n)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) h->error = 4u;
+        return;
+    }
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < in.n) {
+        char *rec = prims + (uint64_t)j * Input::rec_bytes;
+        in.write(rec, Input::record_prim(rec));
+    }
+}
+
+template<class Input>
+__global__ void __launch_bounds__(128) k_refit_climb(RefitCtx c, Input in) {
+    if (!refit_allowed(c.header, in.n)) return;
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w < c.header->node_count) refit_climb(c, in, w);
+}
+
+// ---- instance buffer
+__global__ void k_instances_init(Instance *instances, uint32_t first, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) {
+        Instance in;
+        init_instance(in);
+        copy_vec16(&instances[first + i], &in, 5);
+    }
+}
+__global__ void k_apply_mods(Instance *instances, const Modification *__restrict__ mods, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        Modification m;
+        copy_vec16(&m, &mods[i], 5);
+        apply_modification(instances, m);
+    }
+}
+__global__ void k_update_handles(Instance *instances, const InstanceHandleUpdate *__restrict__ ups, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) apply_handle_update(instances, ups[i]);
+}
+
+// =====================================================================================================================
+// trace kernels
+// =====================================================================================================================
+constexpr int TRACE_BLOCK = 128;
+constexpr int TRACE_SMEM_STACK = 8;   // entries per thread kept in shared memory
+constexpr int TRACE_STEPS = 6;        // traversal steps between refill checks
+constexpr uint32_t TRACE_BATCH = 128; // rays a warp reserves per atomic
+
+struct HybridStack {
+    u2 *smem;// this thread's column: entry i at smem[i * TRACE_BLOCK]
+    u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
+    __device__ __forceinline__ void store(int i, u2 v) {
+        if (i < TRACE_SMEM_STACK) smem[i * TRACE_BLOCK] = v;
+        else local[i - TRACE_SMEM_STACK] = v;
+    }
+    __device__ __forceinline__ u2 load(int i) const { return i < TRACE_SMEM_STACK ? smem[i * TRACE_BLOCK] : local[i - TRACE_SMEM_STACK]; }
+};
+
+struct TraceParams {
+    const BlobHeader *tlas;
+    const Instance *instances;
+    const Ray *rays;
+    uint64_t n;
+    const uint32_t *masks;
+    uint32_t mask;
+    void *out;
+    unsigned long long *next;    // ray cursor (zeroed before the launch)
+    unsigned long long *counters;// optional
+    uint32_t tri_prog, proc_prog;
+    int terminate_on_first;
+};
+
+template<int MODE, bool COUNT, class Callbacks>
+__global__ void __launch_bounds__(TRACE_BLOCK, 4) k_trace(TraceParams p) {
+    __shared__ u2 sstack[TRACE_SMEM_STACK * TRACE_BLOCK];
+    HybridStack stack;
+    stack.smem = sstack + threadIdx.x;
+    Callbacks cb;
+    if constexpr (MODE == MODE_QUERY) cb = Callbacks{p.tri_prog, p.proc_prog};
+    Traversal<MODE, COUNT, HybridStack, Callbacks> tr;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    bool active = false;
+    uint64_t ray_idx = 0;
+    uint64_t warp_next = 0, warp_end = 0;// this warp's reserved range of ray indices
+    unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0;
+    bool exhausted = false;
+    for (;;) {
+        // ---- warp-cooperative refill of idle lanes
+        const uint32_t idle = __ballot_sync(0xffffffffu, !active);
+        if (idle && !exhausted) {
+            const uint32_t want = (uint32_t)__popc(idle);
+            if (warp_end - warp_next < want) {
+                // keep what is left, reserve a fresh batch when the remainder can not serve all idle lanes
+                if (warp_next == warp_end) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(p.next, (unsigned long long)TRACE_BATCH);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    warp_next = base < p.n ? base : p.n;
+                    warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
+                    if (warp_next == warp_end) exhausted = true;
+                }
+            }
+            const uint64_t avail = warp_end - warp_next;
+            const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
+            if (!active && rank < avail) {
+                ray_idx = warp_next + rank;
+                const f4 *rp = reinterpret_cast<const f4 *>(p.rays + ray_idx);
+                const f4 r0 = rp[0], r1 = rp[1];
+                Ray ray;
+                ray.ox = r0.x, ray.oy = r0.y, ray.oz = r0.z, ray.tmin = r0.w, ray.dx = r1.x, ray.dy = r1.y, ray.dz = r1.z, ray.tmax = r1.w;
+                tr.init(p.tlas, p.instances, ray, p.masks ? p.masks[ray_idx] : p.mask, &stack, &cb);
+                if constexpr (MODE == MODE_QUERY) tr.terminate_on_first = p.terminate_on_first != 0;
+                active = true;
+            }
+            warp_next += want < avail ? want : avail;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        // ---- a bounded number of traversal steps
+        if (active) {
+#pragma unroll 1
+            for (int k = 0; k < TRACE_STEPS; k++) {
+                if (!tr.step()) {
+                    if constexpr (MODE == MODE_CLOSEST) {
+                        SurfaceHit h;
+                        const bool hit = tr.hit_inst != ~0u;
+                        h.inst = tr.hit_inst, h.prim = tr.hit_prim, h.u = tr.hit_u, h.v = tr.hit_v;
+                        h.t = hit ? (float)tr.t_best : tr.world.tmax, h.pad = 0u;
+                        u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
+                        o[0] = make_u2(h.inst, h.prim), o[1] = make_u2(as_uint(h.u), as_uint(h.v)), o[2] = make_u2(as_uint(h.t), 0u);
+                    } else if constexpr (MODE == MODE_ANY) {
+                        static_cast<uint32_t *>(p.out)[ray_idx] = tr.hit_inst != ~0u ? 1u : 0u;
+                    } else {
+                        const bool hit = tr.hit_type != HIT_MISS;
+                        u2 *o = reinterpret_cast<u2 *>(static_cast<CommittedHit *>(p.out) + ray_idx);
+                        o[0] = make_u2(tr.hit_inst, tr.hit_prim), o[1] = make_u2(as_uint(tr.hit_u), as_uint(tr.hit_v));
+                        o[2] = make_u2(tr.hit_type, as_uint(hit ? (float)tr.t_best : tr.world.tmax));
+                    }
+                    if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts;
+                    active = false;
+                    break;
+                }
+            }
+        }
+    }
+    if constexpr (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_nodes += __shfl_xor_sync(0xffffffffu, c_nodes, o);
+            c_prims += __shfl_xor_sync(0xffffffffu, c_prims, o);
+            c_insts += __shfl_xor_sync(0xffffffffu, c_insts, o);
+        }
+        if (lane == 0 && p.counters) {
+            atomicAdd(&p.counters[0], c_nodes);
+            atomicAdd(&p.counters[1], c_prims);
+            atomicAdd(&p.counters[2], c_insts);
+        }
+    }
+}
+
+// =====================================================================================================================
+// host side
+// =====================================================================================================================
+static thread_local char g_last_cuda_error[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what) {
+    snprintf(g_last_cuda_error, sizeof(g_last_cuda_error), "%s: %s", what, cudaGetErrorString(e));
+    return LCRT_ERROR_CUDA;
+}
+#define LCRT_CUDA(call)                                     \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+    } while (0)
+#define LCRT_LAUNCH_CHECK(name)                            \
+    do {                                                   \
+        cudaError_t e_ = cudaGetLastError();               \
+        if (e_ != cudaSuccess) return cuda_fail(e_, name); \
+    } while (0)
+
+struct DeviceInfo {
+    int sm_count = 0;
+    unsigned long long *cursors = nullptr;// ring of ray cursors
+    int collapse_blocks_per_sm[3] = {0, 0, 0};
+    int trace_blocks_per_sm = 0;
+};
+constexpr int CURSOR_RING = 4096;
+static std::mutex g_dev_mutex;
+static DeviceInfo g_dev[64];
+static std::atomic<uint32_t> g_cursor_next{0};
+
+static int device_info(DeviceInfo **out) {
+    int dev = 0;
+    LCRT_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return LCRT_ERROR_INVALID_VALUE;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceInfo &d = g_dev[dev];
+    if (d.sm_count == 0) {
+        int sms = 0;
+        LCRT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        LCRT_CUDA(cudaMalloc(&d.cursors, CURSOR_RING * sizeof(unsigned long long)));
+        d.sm_count = sms;
+    }
+    *out = &d;
+    return LCRT_SUCCESS;
+}
+
+static float sah_ci(uint32_t flags) {
+    static const char *env = getenv("LCRT_SAH_CI");
+    if (env) return (float)atof(env);
+    return (flags & BUILD_FAST_BUILD) ? 1.0f : 0.5f;
+}
+
+template<class Input>
+static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, void *temp, uint64_t temp_bytes, void *blob, uint64_t blob_bytes) {
+    const uint32_t n = in.n;
+    const BlobLayout L = blob_layout(Input::kind, n, flags);
+    const TempLayout T = temp_layout(n, L.node_capacity);
+    if (blob == nullptr || blob_bytes < L.total_bytes) return LCRT_ERROR_BUFFER_TOO_SMALL;
+    if (temp == nullptr || temp_bytes < T.total_bytes) return LCRT_ERROR_BUFFER_TOO_SMALL;
+    if ((reinterpret_cast<uintptr_t>(blob) & 127u) || (reinterpret_cast<uintptr_t>(temp) & 127u)) return LCRT_ERROR_MISALIGNED;
+    DeviceInfo *dev;
+    if (int rc = device_info(&dev)) return rc;
+    char *tp = static_cast<char *>(temp);
+    char *bp = static_cast<char *>(blob);
+    uint32_t *small = reinterpret_cast<uint32_t *>(tp + T.small);
+    BlobHeader *h = reinterpret_cast<BlobHeader *>(bp);
+    k_build_init<<<1, 32, 0, stream>>>(h, Input::kind, n, flags, L, small);
+    LCRT_LAUNCH_CHECK("k_build_init");
+    if (n == 0) return LCRT_SUCCESS;
+    uint32_t *flag = reinterpret_cast<uint32_t *>(tp + T.flag);
+    uint32_t *task = reinterpret_cast<uint32_t *>(tp + T.task);
+    LCRT_CUDA(cudaMemsetAsync(flag, 0, (uint64_t)n * 4, stream));
+    LCRT_CUDA(cudaMemsetAsync(task, 0xff, (uint64_t)L.node_capacity * 4, stream));
+    const uint32_t blocks256 = (n + 255u) / 256u;
+    {
+        const uint32_t g = blocks256 < (uint32_t)dev->sm_count * 8u ? blocks256 : (uint32_t)dev->sm_count * 8u;
+        k_centroid_bounds<Input><<<g, 256, 0, stream>>>(in, small);
+        LCRT_LAUNCH_CHECK("k_centroid_bounds");
+    }
+    SortBuffers sb;
+    sb.keys[0] = reinterpret_cast<uint64_t *>(tp + T.keys0), sb.keys[1] = reinterpret_cast<uint64_t *>(tp + T.keys1);
+    sb.vals[0] = reinterpret_cast<uint32_t *>(tp + T.vals0), sb.vals[1] = reinterpret_cast<uint32_t *>(tp + T.vals1);
+    sb.table = reinterpret_cast<uint32_t *>(tp + T.hist);
+    sb.sums = sb.table + 256ull * T.sort_blocks;
+    const uint32_t bits = morton_bits_for(n);
+    k_morton<Input><<<blocks256, 256, 0, stream>>>(in, small, sb.keys[0], sb.vals[0], bits);
+    LCRT_LAUNCH_CHECK("k_morton");
+    const int cur = radix_sort_pairs(stream, sb, n, 3u * bits);
+    LCRT_LAUNCH_CHECK("radix_sort_pairs");
+    Bvh2 t;
+    t.n = n, t.keys = sb.keys[cur], t.order = sb.vals[cur];
+    t.lo = reinterpret_cast<f4 *>(tp + T.lo), t.hi = reinterpret_cast<f4 *>(tp + T.hi);
+    t.child = reinterpret_cast<u2 *>(tp + T.child), t.range = reinterpret_cast<u2 *>(tp + T.range);
+    t.flag = flag, t.root = small + SM_ROOT, t.ci = sah_ci(flags), t.max_leaf = Input::max_leaf;
+    k_climb<Input><<<blocks256, 256, 0, stream>>>(t, in);
+    LCRT_LAUNCH_CHECK("k_climb");
+    Bvh8Out o;
+    o.header = h, o.nodes = reinterpret_cast<Node8 *>(bp + L.nodes_offset), o.prims = bp + L.prims_offset;
+    o.parent = L.parent_offset ? reinterpret_cast<uint32_t *>(bp + L.parent_offset) : nullptr;
+    o.task = task, o.counters = small + SM_COUNTERS, o.node_capacity = L.node_capacity;
+    {
+        int &bps = dev->collapse_blocks_per_sm[Input::kind];
+        if (bps == 0) {
+            LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_collapse<Input>, 128, 0));
+            if (bps < 1) bps = 1;
+        }
+        uint32_t g = (uint32_t)(dev->sm_count * bps);
+        const uint32_t need = (L.node_capacity + 127u) / 128u;
+        if (g > need) g = need;
+        k_collapse<Input><<<g, 128, 0, stream>>>(t, o, in, small + SM_ABORT);
+        LCRT_LAUNCH_CHECK("k_collapse");
+    }
+    k_build_finalize<<<1, 32, 0, stream>>>(h, small, n);
+    LCRT_LAUNCH_CHECK("k_build_finalize");
+    return LCRT_SUCCESS;
+}
+
+template<class Input>
+static int refit_generic(cudaStream_t stream, const Input &in, void *temp, uint64_t temp_bytes, void *blob) {
+    // the header lives on the device; sizes are derived from the primitive count the caller states (validated on
+    // the device: a mismatching blob makes the kernels no-ops through node_count / prim_count checks)
+    const uint32_t n = in.n;
+    const BlobLayout L = blob_layout(Input::kind, n, BUILD_ALLOW_UPDATE);
+    if (blob == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    if (temp == nullptr || temp_bytes < refit_temp_bytes(L.node_capacity)) return LCRT_ERROR_BUFFER_TOO_SMALL;
+    if (n == 0) return LCRT_SUCCESS;
+    char *bp = static_cast<char *>(blob);
+    char *tp = static_cast<char *>(temp);
+    RefitCtx c;
+    c.header = reinterpret_cast<BlobHeader *>(bp);
+    c.nodes = reinterpret_cast<Node8 *>(bp + L.nodes_offset), c.prims = bp + L.prims_offset;
+    c.parent = reinterpret_cast<const uint32_t *>(bp + L.parent_offset);
+    c.box_lo = reinterpret_cast<f4 *>(tp), c.box_hi = c.box_lo + L.node_capacity;
+    c.arrived = reinterpret_cast<uint32_t *>(c.box_hi + L.node_capacity);
+    LCRT_CUDA(cudaMemsetAsync(c.arrived, 0, (uint64_t)L.node_capacity * 4, stream));
+    k_refit_records<Input><<<(n + 255u) / 256u, 256, 0, stream>>>(in, c.header, c.prims);
+    LCRT_LAUNCH_CHECK("k_refit_records");
+    k_refit_climb<Input><<<(L.node_capacity + 127u) / 128u, 128, 0, stream>>>(c, in);
+    LCRT_LAUNCH_CHECK("k_refit_climb");
+    return LCRT_SUCCESS;
+}
+
+template<int MODE, class Callbacks>
+static int trace_generic(cudaStream_t stream, const void *tlas, const void *instances, const void *rays, uint64_t n, const uint32_t *masks,
+                         uint32_t mask, void *out, uint64_t *counters, uint32_t tri_prog, uint32_t proc_prog, int terminate_on_first) {
+    if (n == 0) return LCRT_SUCCESS;
+    if (tlas == nullptr || rays == nullptr || out == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    if (reinterpret_cast<uintptr_t>(rays) & 15u) return LCRT_ERROR_MISALIGNED;
+    if (reinterpret_cast<uintptr_t>(out) & 7u) return LCRT_ERROR_MISALIGNED;
+    DeviceInfo *dev;
+    if (int rc = device_info(&dev)) return rc;
+    TraceParams p;
+    p.tlas = static_cast<const BlobHeader *>(tlas), p.instances = static_cast<const Instance *>(instances);
+    p.rays = static_cast<const Ray *>(rays), p.n = n, p.masks = masks, p.mask = mask, p.out = out;
+    p.next = dev->cursors + (g_cursor_next.fetch_add(1) % CURSOR_RING);
+    p.counters = reinterpret_cast<unsigned long long *>(counters);
+    p.tri_prog = tri_prog, p.proc_prog = proc_prog, p.terminate_on_first = terminate_on_first;
+    LCRT_CUDA(cudaMemsetAsync(p.next, 0, sizeof(unsigned long long), stream));
+    int bps = 0;
+    if (counters) {
+        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, true, Callbacks>, TRACE_BLOCK, 0));
+    } else {
+        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, false, Callbacks>, TRACE_BLOCK, 0));
+    }
+    if (bps < 1) bps = 1;
+    uint64_t g = (uint64_t)dev->sm_count * (uint64_t)bps;
+    const uint64_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
+    if (g > need) g = need;
+    if (counters) k_trace<MODE, true, Callbacks><<<(uint32_t)g, TRACE_BLOCK, 0, stream>>>(p);
+    else k_trace<MODE, false, Callbacks><<<(uint32_t)g, TRACE_BLOCK, 0, stream>>>(p);
+    LCRT_LAUNCH_CHECK("k_trace");
+    return LCRT_SUCCESS;
+}
+
+}// namespace lcrt
+
+// =====================================================================================================================
+// C-ABI
+// =====================================================================================================================
+using namespace lcrt;
+
+extern "C" {
+
+int lcrtGetVersion(void) { return 100; }
+
+const char *lcrtGetErrorString(int code) {
+    switch (code) {
+        case LCRT_SUCCESS: return "success";
+        case LCRT_ERROR_INVALID_VALUE: return "invalid value";
+        case LCRT_ERROR_BUFFER_TOO_SMALL: return "buffer too small";
+        case LCRT_ERROR_CUDA: return "CUDA error (see lcrtGetLastCudaError)";
+        case LCRT_ERROR_NOT_UPDATABLE: return "acceleration structure was not built with LCRT_BUILD_ALLOW_UPDATE";
+        case LCRT_ERROR_MISALIGNED: return "misaligned pointer";
+        default: return "unknown error";
+    }
+}
+
+const char *lcrtGetLastCudaError(void) { return g_last_cuda_error; }
+
+int lcrtAccelComputeMemoryUsage(uint32_t kind, uint32_t prim_count, uint32_t flags, lcrtSizes *out) {
+    if (out == nullptr || kind > KIND_INSTANCES) return LCRT_ERROR_INVALID_VALUE;
+    const BlobLayout L = blob_layout(kind, prim_count, flags);
+    const TempLayout T = temp_layout(prim_count, L.node_capacity);
+    out->blob_bytes = L.total_bytes;
+    out->build_temp_bytes = T.total_bytes;
+    out->update_temp_bytes = (flags & BUILD_ALLOW_UPDATE) ? refit_temp_bytes(L.node_capacity) : 0;
+    return LCRT_SUCCESS;
+}
+
+int lcrtBuildTriangles(lcrtStream stream, const void *vertices, uint64_t vertex_stride, const void *triangles, uint32_t triangle_count,
+                       uint32_t flags, void *temp, uint64_t temp_bytes, void *blob, uint64_t blob_bytes) {
+    if (triangle_count && (vertices == nullptr || triangles == nullptr)) return LCRT_ERROR_INVALID_VALUE;
+    if (vertex_stride < 12 || (vertex_stride & 3u)) return LCRT_ERROR_INVALID_VALUE;
+    TriInput in{static_cast<const char *>(vertices), vertex_stride, static_cast<const uint32_t *>(triangles), triangle_count};
+    return build_generic(static_cast<cudaStream_t>(stream), in, flags, temp, temp_bytes, blob, blob_bytes);
+}
+
+int lcrtRefitTriangles(lcrtStream stream, const void *vertices, uint64_t vertex_stride, const void *triangles, uint32_t triangle_count,
+                       void *temp, uint64_t temp_bytes, void *blob) {
+    if (triangle_count && (vertices == nullptr || triangles == nullptr)) return LCRT_ERROR_INVALID_VALUE;
+    if (vertex_stride < 12 || (vertex_stride & 3u)) return LCRT_ERROR_INVALID_VALUE;
+    TriInput in{static_cast<const char *>(vertices), vertex_stride, static_cast<const uint32_t *>(triangles), triangle_count};
+    return refit_generic(static_cast<cudaStream_t>(stream), in, temp, temp_bytes, blob);
+}
+
+int lcrtBuildAabbs(lcrtStream stream, const void *aabbs, uint32_t aabb_count, uint32_t flags, void *temp, uint64_t temp_bytes, void *blob,
+                   uint64_t blob_bytes) {
+    if (aabb_count && aabbs == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    AabbInput in{static_cast<const float *>(aabbs), aabb_count};
+    return build_generic(static_cast<cudaStream_t>(stream), in, flags, temp, temp_bytes, blob, blob_bytes);
+}
+
+int lcrtRefitAabbs(lcrtStream stream, const void *aabbs, uint32_t aabb_count, void *temp, uint64_t temp_bytes, void *blob) {
+    if (aabb_count && aabbs == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    AabbInput in{static_cast<const float *>(aabbs), aabb_count};
+    return refit_generic(static_cast<cudaStream_t>(stream), in, temp, temp_bytes, blob);
+}
+
+int lcrtInstancesInit(lcrtStream stream, void *instances, uint32_t first, uint32_t count) {
+    if (count == 0) return LCRT_SUCCESS;
+    if (instances == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    k_instances_init<<<(count + 255u) / 256u, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<Instance *>(instances), first, count);
+    LCRT_LAUNCH_CHECK("k_instances_init");
+    return LCRT_SUCCESS;
+}
+
+int lcrtInstancesApplyMods(lcrtStream stream, void *instances, const void *mods_device, uint32_t mod_count) {
+    if (mod_count == 0) return LCRT_SUCCESS;
+    if (instances == nullptr || mods_device == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    // same launch shape as the reference: 256 threads per block, one thread per modification (cuda_accel.cpp:234-238)
+    k_apply_mods<<<(mod_count + 255u) / 256u, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<Instance *>(instances),
+                                                                                             static_cast<const Modification *>(mods_device), mod_count);
+    LCRT_LAUNCH_CHECK("k_apply_mods");
+    return LCRT_SUCCESS;
+}
+
+int lcrtInstancesUpdateHandles(lcrtStream stream, void *instances, const void *updates_device, uint32_t count) {
+    if (count == 0) return LCRT_SUCCESS;
+    if (instances == nullptr || updates_device == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    k_update_handles<<<(count + 255u) / 256u, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<Instance *>(instances), static_cast<const InstanceHandleUpdate *>(updates_device), count);
+    LCRT_LAUNCH_CHECK("k_update_handles");
+    return LCRT_SUCCESS;
+}
+
+int lcrtBuildTlas(lcrtStream stream, const void *instances, uint32_t instance_count, uint32_t flags, void *temp, uint64_t temp_bytes,
+                  void *blob, uint64_t blob_bytes) {
+    if (instance_count == 0 || instances == nullptr) return LCRT_ERROR_INVALID_VALUE;// cuda_accel.cpp:159
+    InstInput in{static_cast<const Instance *>(instances), instance_count};
+    return build_generic(static_cast<cudaStream_t>(stream), in, flags, temp, temp_bytes, blob, blob_bytes);
+}
+
+int lcrtRefitTlas(lcrtStream stream, const void *instances, uint32_t instance_count, void *temp, uint64_t temp_bytes, void *blob) {
+    if (instance_count == 0 || instances == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    InstInput in{static_cast<const Instance *>(instances), instance_count};
+    return refit_generic(static_cast<cudaStream_t>(stream), in, temp, temp_bytes, blob);
+}
+
+int lcrtTraceClosest(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                     uint32_t mask, void *hits, uint64_t *counters) {
+    return trace_generic<MODE_CLOSEST, NoCallbacks>(static_cast<cudaStream_t>(stream), tlas, instances, rays, ray_count, masks, mask, hits, counters,
+                                                    0, 0, 0);
+}
+
+int lcrtTraceAny(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                 uint32_t mask, uint32_t *occluded, uint64_t *counters) {
+    return trace_generic<MODE_ANY, NoCallbacks>(static_cast<cudaStream_t>(stream), tlas, instances, rays, ray_count, masks, mask, occluded, counters, 0,
+                                                0, 0);
+}
+
+int lcrtQuery(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,
+              uint32_t mask, int terminate_on_first, uint32_t tri_program, uint32_t proc_program, void *hits) {
+    if (tri_program > TRI_TERMINATE_FIRST || proc_program > PROC_IGNORE_ALL) return LCRT_ERROR_INVALID_VALUE;
+    if (instances == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    return trace_generic<MODE_QUERY, BuiltinPrograms>(static_cast<cudaStream_t>(stream), tlas, instances, rays, ray_count, masks, mask, hits, nullptr,
+                                                      tri_program, proc_program, terminate_on_first);
+}
+
+int lcrtBlobGetInfo(lcrtStream stream, const void *blob, lcrtBlobInfo *out) {
+    if (blob == nullptr || out == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    BlobHeader h;
+    LCRT_CUDA(cudaMemcpyAsync(&h, blob, sizeof(h), cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    LCRT_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    if (h.magic != BLOB_MAGIC) return LCRT_ERROR_INVALID_VALUE;
+    out->kind = h.kind, out->prim_count = h.prim_count, out->node_count = h.node_count, out->node_capacity = h.node_capacity;
+    out->built = h.built, out->error = h.error, out->flags = h.flags, out->prim_stride = h.prim_stride;
+    for (int a = 0; a < 3; a++) out->lo[a] = h.lo[a], out->hi[a] = h.hi[a];
+    out->nodes_offset = h.nodes_offset, out->prims_offset = h.prims_offset, out->total_bytes = h.total_bytes;
+    return LCRT_SUCCESS;
+}
+
+uint64_t lcrtSortTempBytes(uint32_t n) {
+    const uint64_t nn = n ? n : 1;
+    return align_up(nn * 8, 256) + align_up(nn * 4, 256) + align_up(sort_table_bytes(n), 256);
+}
+
+int lcrtSortPairs(lcrtStream stream_, uint64_t *keys, uint32_t *values, uint32_t n, uint32_t key_bits, void *temp, uint64_t temp_bytes) {
+    if (n == 0) return LCRT_SUCCESS;
+    if (keys == nullptr || values == nullptr || temp == nullptr || key_bits == 0 || key_bits > 64) return LCRT_ERROR_INVALID_VALUE;
+    if (temp_bytes < lcrtSortTempBytes(n)) return LCRT_ERROR_BUFFER_TOO_SMALL;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    char *tp = static_cast<char *>(temp);
+    SortBuffers sb;
+    sb.keys[0] = keys, sb.vals[0] = values;
+    sb.keys[1] = reinterpret_cast<uint64_t *>(tp);
+    sb.vals[1] = reinterpret_cast<uint32_t *>(tp + align_up((uint64_t)n * 8, 256));
+    sb.table = reinterpret_cast<uint32_t *>(tp + align_up((uint64_t)n * 8, 256) + align_up((uint64_t)n * 4, 256));
+    const uint32_t ntiles = (n + SORT_TILE_KEYS - 1) / SORT_TILE_KEYS;
+    sb.sums = sb.table + 256ull * ntiles;
+    const int cur = radix_sort_pairs(stream, sb, n, key_bits);
+    LCRT_LAUNCH_CHECK("radix_sort_pairs");
+    if (cur == 1) {
+        LCRT_CUDA(cudaMemcpyAsync(keys, sb.keys[1], (uint64_t)n * 8, cudaMemcpyDeviceToDevice, stream));
+        LCRT_CUDA(cudaMemcpyAsync(values, sb.vals[1], (uint64_t)n * 4, cudaMemcpyDeviceToDevice, stream));
+    }
+    return LCRT_SUCCESS;
+}
+
+extern const char lcrt_device_library_text[];
+const char *lcrtDeviceLibrarySource(void) { return lcrt_device_library_text; }
+
+}// extern "C"

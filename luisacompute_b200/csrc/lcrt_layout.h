@@ -62,7 +62,10 @@ inline TempLayout temp_layout(uint32_t n, uint32_t node_capacity) {
     t.task = take((uint64_t)node_capacity * 4);
     t.keys0 = take(nn * 8), t.keys1 = take(nn * 8);
     t.vals0 = take(nn * 4), t.vals1 = take(nn * 4);
-    t.hist = take((uint64_t)t.sort_blocks * 256 * 4 + 256 * 4);
+    {
+        const uint64_t m = 256ull * t.sort_blocks;
+        t.hist = take((m + (m + 2047) / 2048 + 64) * 4);// digit-major table followed by the scan's tile sums
+    }
     t.lo = take((2 * nn) * 16), t.hi = take((2 * nn) * 16);
     t.child = take(nn * 8), t.range = take(nn * 8);
     t.total_bytes = off;

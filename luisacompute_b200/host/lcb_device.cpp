@@ -1,0 +1,498 @@
+// lcb_device.cpp — host-side device layer (C++), the counterpart of the reference's CUDA backend host classes for
+// the ray-tracing path.  It owns no kernels: all device work goes through the thin kernel C-ABI (include/lcb200_rt.h).
+//
+// Class-by-class correspondence (paths relative to /root/reference):
+//   Primitive / Mesh / ProceduralPrimitive  <- CUDAPrimitive / CUDAMesh / CUDAProceduralPrimitive
+//        src/backends/cuda/cuda_primitive.cpp:20-132, cuda_mesh.cpp:31-69, cuda_procedural_primitive.cpp:26-55
+//   Accel                                   <- CUDAAccel  src/backends/cuda/cuda_accel.cpp:152-318
+//   Device                                  <- CUDADevice (create_mesh & co.)  src/backends/cuda/cuda_device.cpp:909-981
+// Differences by design: no host stall for compaction (cuda_primitive.cpp:74, cuda_accel.cpp:90), scratch and blobs
+// come from the stream-ordered pool (cudaMallocAsync) and are reused across rebuilds of the same size.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/lcb200_device.h"
+#include "../csrc/lcrt_common.h"
+
+namespace lcb {
+
+using lcrt::Modification;
+
+#define LCB_CHECK(expr)                                                                                   \
+    do {                                                                                                  \
+        int rc_ = (expr);                                                                                 \
+        if (rc_ != 0) {                                                                                   \
+            fprintf(stderr, "[lcb200] %s failed: %s (%s) at %s:%d\n", #expr, lcrtGetErrorString(rc_),     \
+                    lcrtGetLastCudaError(), __FILE__, __LINE__);                                          \
+            return rc_;                                                                                   \
+        }                                                                                                 \
+    } while (0)
+#define LCB_CUDA(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess) {                                                                          \
+            fprintf(stderr, "[lcb200] %s failed: %s at %s:%d\n", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return LCRT_ERROR_CUDA;                                                                       \
+        }                                                                                                 \
+    } while (0)
+
+static uint32_t build_flags(const lcbAccelOption &o) {
+    uint32_t f = 0;
+    if (o.hint == 1u) f |= LCRT_BUILD_FAST_BUILD;
+    if (o.allow_update) f |= LCRT_BUILD_ALLOW_UPDATE;
+    if (o.allow_compaction) f |= LCRT_BUILD_ALLOW_COMPACTION;
+    return f;
+}
+
+struct Resource {
+    enum class Tag { MESH, PROCEDURAL, ACCEL };
+    Tag tag;
+    lcbAccelOption option;
+    std::mutex mutex;
+    void *blob = nullptr;
+    uint64_t blob_bytes = 0;
+    void *temp = nullptr;// kept between builds of the same size (test_rtx rebuilds every frame, test_rtx.cpp:122-139)
+    uint64_t temp_bytes = 0;
+    int last_build_kind = 0;
+    explicit Resource(Tag t, const lcbAccelOption &o) : tag{t}, option{o} {}
+    virtual ~Resource() {
+        if (blob) cudaFree(blob);
+        if (temp) cudaFree(temp);
+    }
+    uint64_t native() const { return reinterpret_cast<uint64_t>(blob); }
+
+    int ensure(cudaStream_t stream, uint64_t need_blob, uint64_t need_temp) {
+        if (blob_bytes < need_blob || blob_bytes > need_blob * 2 + (1u << 20)) {
+            if (blob) LCB_CUDA(cudaFreeAsync(blob, stream));
+            blob = nullptr, blob_bytes = 0;
+            LCB_CUDA(cudaMallocAsync(&blob, need_blob, stream));
+            blob_bytes = need_blob;
+        }
+        if (temp_bytes < need_temp || temp_bytes > need_temp * 2 + (1u << 20)) {
+            if (temp) LCB_CUDA(cudaFreeAsync(temp, stream));
+            temp = nullptr, temp_bytes = 0;
+            LCB_CUDA(cudaMallocAsync(&temp, need_temp, stream));
+            temp_bytes = need_temp;
+        }
+        return 0;
+    }
+};
+
+struct Primitive : Resource {
+    using Resource::Resource;
+    bool built = false;
+};
+
+struct Mesh final : Primitive {
+    uint64_t vertex_buffer = 0, vertex_buffer_size = 0, vertex_stride = 0, triangle_buffer = 0, triangle_buffer_size = 0;
+    explicit Mesh(const lcbAccelOption &o) : Primitive{Tag::MESH, o} {}
+
+    int build(cudaStream_t stream, const lcbMeshBuildCommand &c) {
+        std::scoped_lock lock{mutex};
+        const uint64_t vb = c.vertex_buffer + c.vertex_buffer_offset, tb = c.triangle_buffer + c.triangle_buffer_offset;
+        // cuda_mesh.cpp:42-54
+        const bool requires_build = !built || !option.allow_update || c.request == LCB_BUILD_FORCE_BUILD || vb != vertex_buffer ||
+                                    c.vertex_buffer_size != vertex_buffer_size || c.vertex_stride != vertex_stride || tb != triangle_buffer ||
+                                    c.triangle_buffer_size != triangle_buffer_size;
+        vertex_buffer = vb, vertex_buffer_size = c.vertex_buffer_size, vertex_stride = c.vertex_stride;
+        triangle_buffer = tb, triangle_buffer_size = c.triangle_buffer_size;
+        if (vertex_stride < 12 || (vertex_stride % 4) != 0) {
+            fprintf(stderr, "[lcb200] invalid vertex stride %llu\n", (unsigned long long)vertex_stride);
+            return LCRT_ERROR_INVALID_VALUE;
+        }
+        const uint32_t n = (uint32_t)(triangle_buffer_size / 12u);// sizeof(Triangle), cuda_mesh.cpp:25-26
+        const uint32_t flags = build_flags(option);
+        lcrtSizes sz;
+        LCB_CHECK(lcrtAccelComputeMemoryUsage(LCRT_KIND_TRIANGLES, n, flags, &sz));
+        if (requires_build) {
+            LCB_CHECK(ensure(stream, sz.blob_bytes, sz.build_temp_bytes > sz.update_temp_bytes ? sz.build_temp_bytes : sz.update_temp_bytes));
+            LCB_CHECK(lcrtBuildTriangles(stream, reinterpret_cast<const void *>(vb), vertex_stride, reinterpret_cast<const void *>(tb), n, flags, temp,
+                                         temp_bytes, blob, blob_bytes));
+            built = true, last_build_kind = 1;
+        } else {
+            LCB_CHECK(lcrtRefitTriangles(stream, reinterpret_cast<const void *>(vb), vertex_stride, reinterpret_cast<const void *>(tb), n, temp,
+                                         temp_bytes, blob));
+            last_build_kind = 2;
+        }
+        return 0;
+    }
+};
+
+struct ProceduralPrimitive final : Primitive {
+    uint64_t aabb_buffer = 0, aabb_buffer_size = 0;
+    explicit ProceduralPrimitive(const lcbAccelOption &o) : Primitive{Tag::PROCEDURAL, o} {}
+
+    int build(cudaStream_t stream, const lcbProceduralPrimitiveBuildCommand &c) {
+        std::scoped_lock lock{mutex};
+        const uint64_t ab = c.aabb_buffer + c.aabb_buffer_offset;
+        // cuda_procedural_primitive.cpp:33-43
+        const bool requires_build = !built || !option.allow_update || c.request == LCB_BUILD_FORCE_BUILD || ab != aabb_buffer ||
+                                    c.aabb_buffer_size != aabb_buffer_size;
+        aabb_buffer = ab, aabb_buffer_size = c.aabb_buffer_size;
+        const uint32_t n = (uint32_t)(aabb_buffer_size / 24u);// sizeof(AABB), cuda_procedural_primitive.cpp:17-19
+        const uint32_t flags = build_flags(option);
+        lcrtSizes sz;
+        LCB_CHECK(lcrtAccelComputeMemoryUsage(LCRT_KIND_AABBS, n, flags, &sz));
+        if (requires_build) {
+            LCB_CHECK(ensure(stream, sz.blob_bytes, sz.build_temp_bytes > sz.update_temp_bytes ? sz.build_temp_bytes : sz.update_temp_bytes));
+            LCB_CHECK(lcrtBuildAabbs(stream, reinterpret_cast<const void *>(ab), n, flags, temp, temp_bytes, blob, blob_bytes));
+            built = true, last_build_kind = 1;
+        } else {
+            LCB_CHECK(lcrtRefitAabbs(stream, reinterpret_cast<const void *>(ab), n, temp, temp_bytes, blob));
+            last_build_kind = 2;
+        }
+        return 0;
+    }
+};
+
+static uint64_t next_pow2(uint64_t v) {
+    uint64_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct Accel final : Resource {
+    void *instance_buffer = nullptr;
+    uint64_t instance_buffer_size = 0;// bytes
+    uint32_t initialised_instances = 0;
+    std::vector<const Primitive *> primitives;
+    std::vector<uint64_t> prim_handles;
+    bool requires_rebuild = true;
+    bool built = false;
+    explicit Accel(const lcbAccelOption &o) : Resource{Tag::ACCEL, o} {}
+    ~Accel() override {
+        if (instance_buffer) cudaFree(instance_buffer);
+    }
+
+    int build(cudaStream_t stream, const lcbAccelBuildCommand &c, const std::unordered_map<uint64_t, std::unique_ptr<Resource>> &resources) {
+        std::scoped_lock lock{mutex};
+        const uint32_t instance_count = c.instance_count;
+        if (instance_count == 0u) {// cuda_accel.cpp:159
+            fprintf(stderr, "[lcb200] Instance count must be greater than 0.\n");
+            return LCRT_ERROR_INVALID_VALUE;
+        }
+        // ---- instance buffer growth to the next power of two, old contents preserved (cuda_accel.cpp:160-170)
+        if (const uint64_t size = (uint64_t)instance_count * sizeof(lcrt::Instance); instance_buffer_size < size) {
+            void *old = instance_buffer;
+            const uint64_t new_size = next_pow2(size);
+            LCB_CUDA(cudaMallocAsync(&instance_buffer, new_size, stream));
+            if (old) {
+                LCB_CUDA(cudaMemcpyAsync(instance_buffer, old, instance_buffer_size, cudaMemcpyDeviceToDevice, stream));
+                LCB_CUDA(cudaFreeAsync(old, stream));
+            }
+            instance_buffer_size = new_size;
+        }
+        if (instance_count > initialised_instances) {
+            // fresh slots start as identity / mask 0xff / opaque (accel.rs:284-295)
+            LCB_CHECK(lcrtInstancesInit(stream, instance_buffer, initialised_instances, instance_count - initialised_instances));
+            initialised_instances = instance_count;
+        }
+        const bool instance_count_changed = primitives.size() != instance_count;
+        primitives.resize(instance_count, nullptr);
+        prim_handles.resize(instance_count, 0ull);
+        // ---- upload the modifications and apply them (cuda_accel.cpp:176-240)
+        if (const uint32_t n = c.modification_count) {
+            std::vector<Modification> host(n);
+            memcpy(host.data(), c.modifications, (size_t)n * sizeof(Modification));
+            for (auto &m : host) {
+                if (m.index >= instance_count) {
+                    fprintf(stderr, "[lcb200] modification index %u out of range\n", m.index);
+                    return LCRT_ERROR_INVALID_VALUE;
+                }
+                if (m.flags & lcrt::MOD_PRIMITIVE) {
+                    requires_rebuild = true;
+                    auto it = resources.find(m.primitive);
+                    if (it == resources.end() || it->second->tag == Resource::Tag::ACCEL) {
+                        fprintf(stderr, "[lcb200] modification refers to an unknown primitive handle\n");
+                        return LCRT_ERROR_INVALID_VALUE;
+                    }
+                    auto prim = static_cast<const Primitive *>(it->second.get());
+                    primitives[m.index] = prim;
+                    m.primitive = prim->native();
+                    prim_handles[m.index] = prim->native();
+                    if (prim->tag == Resource::Tag::PROCEDURAL) m.flags |= lcrt::MOD_PROCEDURAL;
+                }
+            }
+            void *update_buffer = nullptr;
+            LCB_CUDA(cudaMallocAsync(&update_buffer, (size_t)n * sizeof(Modification), stream));
+            LCB_CUDA(cudaMemcpyAsync(update_buffer, host.data(), (size_t)n * sizeof(Modification), cudaMemcpyHostToDevice, stream));
+            LCB_CHECK(lcrtInstancesApplyMods(stream, instance_buffer, update_buffer, n));
+            LCB_CUDA(cudaFreeAsync(update_buffer, stream));
+            // `host` is pageable: the copy above has been staged by the runtime before cudaMemcpyAsync returned
+        }
+        // ---- BLAS handles that changed through a rebuild without a modification (cuda_accel.cpp:244-258, 286-308)
+        std::vector<lcrt::InstanceHandleUpdate> changed;
+        for (uint32_t i = 0; i < instance_count; i++) {
+            if (primitives[i] != nullptr && primitives[i]->native() != prim_handles[i]) {
+                changed.push_back({i, primitives[i]->native()});
+                prim_handles[i] = primitives[i]->native();
+            }
+        }
+        // cuda_accel.cpp:261-267
+        requires_rebuild = requires_rebuild || c.request == LCB_BUILD_FORCE_BUILD || !option.allow_update || !built || instance_count_changed ||
+                           !changed.empty();
+        if (!changed.empty()) {
+            void *dbuf = nullptr;
+            const size_t bytes = changed.size() * sizeof(lcrt::InstanceHandleUpdate);
+            LCB_CUDA(cudaMallocAsync(&dbuf, bytes, stream));
+            LCB_CUDA(cudaMemcpyAsync(dbuf, changed.data(), bytes, cudaMemcpyHostToDevice, stream));
+            LCB_CHECK(lcrtInstancesUpdateHandles(stream, instance_buffer, dbuf, (uint32_t)changed.size()));
+            LCB_CUDA(cudaFreeAsync(dbuf, stream));
+        }
+        if (!c.update_instance_buffer_only) {// cuda_accel.cpp:309-317
+            const uint32_t flags = build_flags(option);
+            lcrtSizes sz;
+            LCB_CHECK(lcrtAccelComputeMemoryUsage(LCRT_KIND_INSTANCES, instance_count, flags, &sz));
+            if (requires_rebuild) {
+                LCB_CHECK(ensure(stream, sz.blob_bytes, sz.build_temp_bytes > sz.update_temp_bytes ? sz.build_temp_bytes : sz.update_temp_bytes));
+                LCB_CHECK(lcrtBuildTlas(stream, instance_buffer, instance_count, flags, temp, temp_bytes, blob, blob_bytes));
+                built = true, last_build_kind = 1;
+            } else {
+                LCB_CHECK(lcrtRefitTlas(stream, instance_buffer, instance_count, temp, temp_bytes, blob));
+                last_build_kind = 2;
+            }
+            requires_rebuild = false;
+        }
+        return 0;
+    }
+};
+
+}// namespace lcb
+
+struct lcbDevice {
+    int index = 0;
+    std::mutex mutex;
+    std::unordered_map<uint64_t, std::unique_ptr<lcb::Resource>> resources;
+    // end-to-end helper state
+    cudaStream_t io_streams[2] = {nullptr, nullptr};
+    void *stage_rays[2] = {nullptr, nullptr};
+    void *stage_hits[2] = {nullptr, nullptr};
+    uint64_t stage_capacity = 0;
+
+    template<class T>
+    T *find(uint64_t handle, lcb::Resource::Tag tag) {
+        std::scoped_lock lock{mutex};
+        auto it = resources.find(handle);
+        if (it == resources.end() || it->second->tag != tag) return nullptr;
+        return static_cast<T *>(it->second.get());
+    }
+    lcb::Resource *find_any(uint64_t handle) {
+        std::scoped_lock lock{mutex};
+        auto it = resources.find(handle);
+        return it == resources.end() ? nullptr : it->second.get();
+    }
+    template<class T>
+    uint64_t add(const lcbAccelOption *option) {
+        lcbAccelOption o{0u, 1u, 0u};// AccelOption defaults (resource.h:119-125)
+        if (option) o = *option;
+        auto r = std::make_unique<T>(o);
+        const uint64_t handle = reinterpret_cast<uint64_t>(r.get());// the CUDA backend also uses object addresses
+        std::scoped_lock lock{mutex};
+        resources.emplace(handle, std::move(r));
+        return handle;
+    }
+    void remove(uint64_t handle) {
+        std::unique_ptr<lcb::Resource> victim;
+        {
+            std::scoped_lock lock{mutex};
+            auto it = resources.find(handle);
+            if (it == resources.end()) return;
+            victim = std::move(it->second);
+            resources.erase(it);
+        }
+        cudaSetDevice(index);
+        cudaDeviceSynchronize();// the reference defers destruction to stream callbacks; this layer simply drains
+        victim.reset();
+    }
+};
+
+#define LCB_DEVICE_GUARD(device)                                             \
+    if ((device) == nullptr) return LCRT_ERROR_INVALID_VALUE;                \
+    if (cudaSetDevice((device)->index) != cudaSuccess) return LCRT_ERROR_CUDA
+
+extern "C" {
+
+const char *lcbBackendName(void) { return "b200rt"; }
+
+lcbDevice *lcbDeviceCreate(int device_index) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        fprintf(stderr, "[lcb200] no CUDA device available: this backend has no CPU fallback\n");
+        return nullptr;
+    }
+    if (device_index < 0 || device_index >= count) {
+        fprintf(stderr, "[lcb200] invalid device index %d (have %d)\n", device_index, count);
+        return nullptr;
+    }
+    if (cudaSetDevice(device_index) != cudaSuccess) return nullptr;
+    auto d = new lcbDevice;
+    d->index = device_index;
+    return d;
+}
+
+void lcbDeviceDestroy(lcbDevice *device) {
+    if (!device) return;
+    cudaSetDevice(device->index);
+    cudaDeviceSynchronize();
+    device->resources.clear();
+    for (int i = 0; i < 2; i++) {
+        if (device->stage_rays[i]) cudaFree(device->stage_rays[i]);
+        if (device->stage_hits[i]) cudaFree(device->stage_hits[i]);
+        if (device->io_streams[i]) cudaStreamDestroy(device->io_streams[i]);
+    }
+    delete device;
+}
+
+uint64_t lcbCreateMesh(lcbDevice *device, const lcbAccelOption *option) { return device ? device->add<lcb::Mesh>(option) : ~0ull; }
+void lcbDestroyMesh(lcbDevice *device, uint64_t handle) {
+    if (device) device->remove(handle);
+}
+uint64_t lcbCreateProceduralPrimitive(lcbDevice *device, const lcbAccelOption *option) {
+    return device ? device->add<lcb::ProceduralPrimitive>(option) : ~0ull;
+}
+void lcbDestroyProceduralPrimitive(lcbDevice *device, uint64_t handle) {
+    if (device) device->remove(handle);
+}
+uint64_t lcbCreateAccel(lcbDevice *device, const lcbAccelOption *option) { return device ? device->add<lcb::Accel>(option) : ~0ull; }
+void lcbDestroyAccel(lcbDevice *device, uint64_t handle) {
+    if (device) device->remove(handle);
+}
+
+int lcbMeshBuild(lcbDevice *device, lcrtStream stream, const lcbMeshBuildCommand *command) {
+    LCB_DEVICE_GUARD(device);
+    if (!command) return LCRT_ERROR_INVALID_VALUE;
+    auto m = device->find<lcb::Mesh>(command->handle, lcb::Resource::Tag::MESH);
+    if (!m) return LCRT_ERROR_INVALID_VALUE;
+    return m->build(static_cast<cudaStream_t>(stream), *command);
+}
+
+int lcbProceduralPrimitiveBuild(lcbDevice *device, lcrtStream stream, const lcbProceduralPrimitiveBuildCommand *command) {
+    LCB_DEVICE_GUARD(device);
+    if (!command) return LCRT_ERROR_INVALID_VALUE;
+    auto p = device->find<lcb::ProceduralPrimitive>(command->handle, lcb::Resource::Tag::PROCEDURAL);
+    if (!p) return LCRT_ERROR_INVALID_VALUE;
+    return p->build(static_cast<cudaStream_t>(stream), *command);
+}
+
+int lcbAccelBuild(lcbDevice *device, lcrtStream stream, const lcbAccelBuildCommand *command) {
+    LCB_DEVICE_GUARD(device);
+    if (!command) return LCRT_ERROR_INVALID_VALUE;
+    auto a = device->find<lcb::Accel>(command->handle, lcb::Resource::Tag::ACCEL);
+    if (!a) return LCRT_ERROR_INVALID_VALUE;
+    std::scoped_lock lock{device->mutex};// primitives must not be destroyed while the accel resolves them
+    return a->build(static_cast<cudaStream_t>(stream), *command, device->resources);
+}
+
+int lcbAccelGetBinding(lcbDevice *device, uint64_t accel, lcbAccelBinding *out) {
+    if (!device || !out) return LCRT_ERROR_INVALID_VALUE;
+    auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
+    if (!a) return LCRT_ERROR_INVALID_VALUE;
+    out->handle = a->native(), out->instances = reinterpret_cast<uint64_t>(a->instance_buffer);
+    return 0;
+}
+
+int lcbLastBuildKind(lcbDevice *device, uint64_t handle) {
+    if (!device) return LCRT_ERROR_INVALID_VALUE;
+    auto r = device->find_any(handle);
+    return r ? r->last_build_kind : LCRT_ERROR_INVALID_VALUE;
+}
+
+uint64_t lcbNativeHandle(lcbDevice *device, uint64_t handle) {
+    if (!device) return 0;
+    auto r = device->find_any(handle);
+    return r ? r->native() : 0;
+}
+
+int lcbBlobInfo(lcbDevice *device, lcrtStream stream, uint64_t handle, lcrtBlobInfo *out) {
+    LCB_DEVICE_GUARD(device);
+    auto r = device->find_any(handle);
+    if (!r || !r->blob) return LCRT_ERROR_INVALID_VALUE;
+    return lcrtBlobGetInfo(stream, r->blob, out);
+}
+
+int lcbTraceClosest(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                    uint32_t mask, void *hits, uint64_t *counters) {
+    LCB_DEVICE_GUARD(device);
+    auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
+    if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    return lcrtTraceClosest(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, hits, counters);
+}
+
+int lcbTraceAny(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                uint32_t mask, uint32_t *occluded, uint64_t *counters) {
+    LCB_DEVICE_GUARD(device);
+    auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
+    if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    return lcrtTraceAny(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, occluded, counters);
+}
+
+int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks, uint32_t mask,
+             int terminate_on_first, uint32_t tri_program, uint32_t proc_program, void *hits) {
+    LCB_DEVICE_GUARD(device);
+    auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
+    if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    return lcrtQuery(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, terminate_on_first, tri_program, proc_program, hits);
+}
+
+int lcbTraceClosestHost(lcbDevice *device, uint64_t accel, const void *host_rays, uint64_t ray_count, uint32_t mask, void *host_hits,
+                        uint64_t chunk_rays) {
+    LCB_DEVICE_GUARD(device);
+    auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
+    if (!a || !a->built || (!host_rays && ray_count) || (!host_hits && ray_count)) return LCRT_ERROR_INVALID_VALUE;
+    if (chunk_rays == 0) chunk_rays = 1u << 20;
+    if (device->stage_capacity < chunk_rays) {
+        for (int i = 0; i < 2; i++) {
+            if (device->stage_rays[i]) cudaFree(device->stage_rays[i]);
+            if (device->stage_hits[i]) cudaFree(device->stage_hits[i]);
+            LCB_CUDA(cudaMalloc(&device->stage_rays[i], chunk_rays * sizeof(lcrt::Ray)));
+            LCB_CUDA(cudaMalloc(&device->stage_hits[i], chunk_rays * sizeof(lcrt::SurfaceHit)));
+            if (!device->io_streams[i]) LCB_CUDA(cudaStreamCreateWithFlags(&device->io_streams[i], cudaStreamNonBlocking));
+        }
+        device->stage_capacity = chunk_rays;
+    }
+    // two streams, two staging slots: chunk k's H2D / trace / D2H are ordered on stream k & 1, so the copy of one
+    // chunk overlaps the traversal of the other and PCIe runs in both directions at once
+    uint64_t done = 0;
+    for (uint64_t k = 0; done < ray_count; k++) {
+        const int s = (int)(k & 1u);
+        const uint64_t n = ray_count - done < chunk_rays ? ray_count - done : chunk_rays;
+        cudaStream_t st = device->io_streams[s];
+        LCB_CUDA(cudaMemcpyAsync(device->stage_rays[s], static_cast<const char *>(host_rays) + done * sizeof(lcrt::Ray), n * sizeof(lcrt::Ray),
+                                 cudaMemcpyHostToDevice, st));
+        LCB_CHECK(lcrtTraceClosest(st, a->blob, a->instance_buffer, device->stage_rays[s], n, nullptr, mask, device->stage_hits[s], nullptr));
+        LCB_CUDA(cudaMemcpyAsync(static_cast<char *>(host_hits) + done * sizeof(lcrt::SurfaceHit), device->stage_hits[s], n * sizeof(lcrt::SurfaceHit),
+                                 cudaMemcpyDeviceToHost, st));
+        done += n;
+    }
+    LCB_CUDA(cudaStreamSynchronize(device->io_streams[0]));
+    LCB_CUDA(cudaStreamSynchronize(device->io_streams[1]));
+    return 0;
+}
+
+int lcbSynchronize(lcbDevice *device, lcrtStream stream) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int lcbDownload(lcbDevice *device, lcrtStream stream, uint64_t device_address, void *host, uint64_t bytes) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaMemcpyAsync(host, reinterpret_cast<const void *>(device_address), bytes, cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(stream)));
+    LCB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int lcbUpload(lcbDevice *device, lcrtStream stream, uint64_t device_address, const void *host, uint64_t bytes) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaMemcpyAsync(reinterpret_cast<void *>(device_address), host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
+    LCB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+}// extern "C"

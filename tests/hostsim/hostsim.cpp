@@ -61,7 +61,7 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
     }
     std::vector<uint64_t> keys(n);
     std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; i++) keys[i] = morton63(in.box(i), clo, inv_ext), order[i] = i;
+    for (uint32_t i = 0; i < n; i++) keys[i] = morton63(in.box(i), clo, inv_ext, morton_bits_for(n)), order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
     std::vector<uint64_t> skeys(n);
     for (uint32_t i = 0; i < n; i++) skeys[i] = keys[order[i]];
