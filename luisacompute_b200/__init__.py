@@ -392,7 +392,10 @@ class Accel(_Resource):
     def build(self, request: int = PREFER_UPDATE, update_instance_buffer_only: bool = False):
         if self._instance_count == 0:
             raise LcrtError("Building acceleration structure without instances.")
-        mods = np.concatenate(list(self._mods.values())) if self._mods else np.zeros(0, dtype=scenes.MOD_DTYPE)
+        mods = np.zeros(len(self._mods), dtype=scenes.MOD_DTYPE)     # (np.concatenate would repack the padded 80-byte dtype)
+        for k, m in enumerate(self._mods.values()):
+            mods[k] = m[0]
+        assert mods.dtype.itemsize == 80 and mods.flags["C_CONTIGUOUS"]
         self._mods.clear()
         cmd = _AccelBuildCommand(self.handle, self._instance_count, request, int(update_instance_buffer_only), len(mods),
                                  mods.ctypes.data_as(C.c_void_p) if len(mods) else None)

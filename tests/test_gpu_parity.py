@@ -28,7 +28,7 @@ def test_radix_sort(dev):
         keys = torch.randint(0, 2 ** 62, (n,), dtype=torch.int64, device="cuda", generator=g)
         if bits < 64:
             keys &= (1 << bits) - 1
-        keys[::7] = keys[0]                           # duplicates: stability matters
+        keys[::7] = keys[0].clone()                        # duplicates: stability matters
         vals = torch.arange(n, dtype=torch.int32, device="cuda")
         ref_k, ref_i = torch.sort(keys, stable=True)
         temp = torch.empty(L.lcrtSortTempBytes(n), dtype=torch.uint8, device="cuda")
