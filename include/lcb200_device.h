@@ -103,6 +103,12 @@ LCRT_API int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, cons
 LCRT_API int lcbTraceClosestHost(lcbDevice *device, uint64_t accel, const void *host_rays, uint64_t ray_count, uint32_t mask,
                                  void *host_hits, uint64_t chunk_rays);
 
+/* Serialisable BLAS: a built mesh / procedural primitive is one position-independent blob.  Export copies it into a
+ * caller-provided device buffer (returns the byte count through *bytes; pass dst = NULL to query), import adopts
+ * such a blob (e.g. after an NCCL broadcast from the rank that built it).  Stream-ordered device-to-device copies. */
+LCRT_API int lcbPrimitiveExport(lcbDevice *device, lcrtStream stream, uint64_t handle, void *dst_device, uint64_t capacity, uint64_t *bytes);
+LCRT_API int lcbPrimitiveImport(lcbDevice *device, lcrtStream stream, uint64_t handle, const void *src_device, uint64_t bytes);
+
 LCRT_API int lcbSynchronize(lcbDevice *device, lcrtStream stream);
 /* BufferDownloadCommand / BufferUploadCommand analogues for raw device addresses (synchronous) */
 LCRT_API int lcbDownload(lcbDevice *device, lcrtStream stream, uint64_t device_address, void *host, uint64_t bytes);

@@ -88,6 +88,7 @@ ABI_SYMBOLS = [
     "lcbDestroyProceduralPrimitive", "lcbCreateAccel", "lcbDestroyAccel", "lcbMeshBuild", "lcbProceduralPrimitiveBuild",
     "lcbAccelBuild", "lcbAccelGetBinding", "lcbLastBuildKind", "lcbNativeHandle", "lcbBlobInfo", "lcbTraceClosest", "lcbTraceAny",
     "lcbQuery", "lcbTraceClosestHost", "lcbSynchronize", "lcbDownload", "lcbUpload",
+    "lcbPrimitiveExport", "lcbPrimitiveImport",
 ]
 
 
@@ -147,6 +148,8 @@ def lib():
     L.lcbTraceClosestHost.argtypes = [vp, u64, vp, u64, u32, vp, u64]
     L.lcbSynchronize.argtypes = [vp, vp]
     L.lcbDownload.argtypes = [vp, vp, u64, vp, u64]
+    L.lcbPrimitiveExport.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]
+    L.lcbPrimitiveImport.argtypes = [vp, vp, u64, vp, u64]
     L.lcbUpload.argtypes = [vp, vp, u64, vp, u64]
     _LIB = L
     return L
@@ -256,7 +259,22 @@ class _Resource:
         return b
 
 
-class Mesh(_Resource):
+class _Primitive(_Resource):
+    def export_blob(self):
+        """The built BLAS as one position-independent uint8 device tensor (NCCL-broadcastable, serialisable)."""
+        import torch
+        n = C.c_uint64(0)
+        _check(lib().lcbPrimitiveExport(self.device._h, _stream(), self.handle, None, 0, C.byref(n)), "lcbPrimitiveExport")
+        t = torch.empty(n.value, dtype=torch.uint8, device=self.device.torch_device)
+        _check(lib().lcbPrimitiveExport(self.device._h, _stream(), self.handle, t.data_ptr(), t.numel(), C.byref(n)), "lcbPrimitiveExport")
+        return t
+
+    def import_blob(self, blob):
+        _check(lib().lcbPrimitiveImport(self.device._h, _stream(), self.handle, blob.data_ptr(), blob.numel()), "lcbPrimitiveImport")
+        return self
+
+
+class Mesh(_Primitive):
     """Triangle BLAS over borrowed vertex / triangle buffers (include/luisa/runtime/rtx/mesh.h)."""
     _destroy = "lcbDestroyMesh"
 
@@ -285,7 +303,7 @@ class Mesh(_Resource):
         return self
 
 
-class ProceduralPrimitive(_Resource):
+class ProceduralPrimitive(_Primitive):
     _destroy = "lcbDestroyProceduralPrimitive"
 
     def __init__(self, device: Device, aabbs, option: AccelOption):

@@ -1,0 +1,57 @@
+"""Multi-GPU plumbing: replicated scene, rays sharded by tile.
+
+Nothing like this exists in the reference (no NCCL / MPI anywhere).  One process per GPU; NCCL is used only
+to broadcast the built BLAS blob from the rank that built it and to gather hit records / checksums; there is no
+collective during traversal.  The functions work with any torch.distributed backend (the CPU tests use gloo).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TILE = 65536
+
+
+def tiles_for_rank(n_rays: int, rank: int, world: int, tile: int = TILE) -> np.ndarray:
+    """Indices of the tiles (of `tile` consecutive rays) that `rank` traces: tile j -> rank j mod world."""
+    n_tiles = (n_rays + tile - 1) // tile
+    return np.arange(rank, n_tiles, world, dtype=np.int64)
+
+
+def ray_indices_for_rank(n_rays: int, rank: int, world: int, tile: int = TILE) -> np.ndarray:
+    t = tiles_for_rank(n_rays, rank, world, tile)
+    idx = (t[:, None] * tile + np.arange(tile, dtype=np.int64)[None, :]).reshape(-1)
+    return idx[idx < n_rays]
+
+
+def broadcast_blob(blob, src: int = 0, device=None):
+    """Broadcast a uint8 tensor whose size only `src` knows.  Returns the tensor on every rank."""
+    import torch
+    import torch.distributed as dist
+    rank = dist.get_rank()
+    dev = blob.device if blob is not None else device
+    n = torch.tensor([blob.numel() if rank == src else 0], dtype=torch.int64, device=dev)
+    dist.broadcast(n, src)
+    if rank != src:
+        blob = torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+    dist.broadcast(blob, src)
+    return blob
+
+
+def gather_hits(local_hits, n_rays: int, dst: int = 0, tile: int = TILE):
+    """Gather per-rank hit records ([n_local, 6] int32, tile-sharded) back into ray order on `dst`."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    counts = [len(ray_indices_for_rank(n_rays, r, world, tile)) for r in range(world)]
+    pad = max(counts)
+    buf = torch.zeros((pad, local_hits.shape[1]), dtype=local_hits.dtype, device=local_hits.device)
+    buf[:local_hits.shape[0]] = local_hits
+    out = [torch.zeros_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, out, dst)
+    if rank != dst:
+        return None
+    full = torch.zeros((n_rays, local_hits.shape[1]), dtype=local_hits.dtype, device=local_hits.device)
+    for r in range(world):
+        idx = torch.from_numpy(ray_indices_for_rank(n_rays, r, world, tile)).to(full.device)
+        full[idx] = out[r][:counts[r]]
+    return full

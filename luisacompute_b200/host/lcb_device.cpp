@@ -475,6 +475,34 @@ int lcbTraceClosestHost(lcbDevice *device, uint64_t accel, const void *host_rays
     return 0;
 }
 
+int lcbPrimitiveExport(lcbDevice *device, lcrtStream stream, uint64_t handle, void *dst_device, uint64_t capacity, uint64_t *bytes) {
+    LCB_DEVICE_GUARD(device);
+    auto r = device->find_any(handle);
+    if (!r || r->tag == lcb::Resource::Tag::ACCEL || !r->blob || !bytes) return LCRT_ERROR_INVALID_VALUE;
+    std::scoped_lock lock{r->mutex};
+    *bytes = r->blob_bytes;
+    if (dst_device == nullptr) return 0;
+    if (capacity < r->blob_bytes) return LCRT_ERROR_BUFFER_TOO_SMALL;
+    LCB_CUDA(cudaMemcpyAsync(dst_device, r->blob, r->blob_bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+
+int lcbPrimitiveImport(lcbDevice *device, lcrtStream stream, uint64_t handle, const void *src_device, uint64_t bytes) {
+    LCB_DEVICE_GUARD(device);
+    auto r = device->find_any(handle);
+    if (!r || r->tag == lcb::Resource::Tag::ACCEL || !src_device || bytes < sizeof(lcrt::BlobHeader)) return LCRT_ERROR_INVALID_VALUE;
+    std::scoped_lock lock{r->mutex};
+    auto st = static_cast<cudaStream_t>(stream);
+    if (r->blob) LCB_CUDA(cudaFreeAsync(r->blob, st));
+    r->blob = nullptr, r->blob_bytes = 0;
+    LCB_CUDA(cudaMallocAsync(&r->blob, bytes, st));
+    r->blob_bytes = bytes;
+    LCB_CUDA(cudaMemcpyAsync(r->blob, src_device, bytes, cudaMemcpyDeviceToDevice, st));
+    static_cast<lcb::Primitive *>(r)->built = true;
+    r->last_build_kind = 1;
+    return 0;
+}
+
 int lcbSynchronize(lcbDevice *device, lcrtStream stream) {
     LCB_DEVICE_GUARD(device);
     LCB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));

@@ -585,9 +585,9 @@ struct Tracer {
 
 template<class F>
 void parallel_chunks(uint64_t n, int threads, F &&f) {
-    // 65536-ray chunks handed out by an atomic counter — the scheme of the reference's CPU
-    // dispatcher (src/rust/luisa_compute_backend_impl/src/cpu/stream.rs:185-210).
-    constexpr uint64_t CH = 65536;
+    // fixed-size chunks handed out by an atomic counter — the scheme of the reference's CPU
+    // dispatcher (blocks stolen through an atomic, src/rust/luisa_compute_backend_impl/src/cpu/stream.rs:185-210).
+    constexpr uint64_t CH = 4096;
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
     if (threads <= 0) threads = 1;
     const uint64_t nchunks = (n + CH - 1) / CH;

@@ -1,0 +1,55 @@
+"""World-size-2 gloo test of the multi-GPU plumbing (tile sharding, blob broadcast, hit gather) on CPU tensors."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from luisacompute_b200 import dist as D
+
+
+def test_tiles_partition_all_rays_exactly_once():
+    for n, world, tile in ((1000, 2, 64), (65536 * 5 + 17, 4, 65536), (10, 8, 4), (64 << 20, 8, 65536)):
+        seen = np.zeros(n, dtype=np.int32) if n < (1 << 22) else None
+        total = 0
+        for r in range(world):
+            idx = D.ray_indices_for_rank(n, r, world, tile)
+            total += len(idx)
+            if seen is not None:
+                seen[idx] += 1
+        assert total == n
+        if seen is not None:
+            assert np.all(seen == 1)
+    # 64 Mi rays over 8 GPUs: every rank gets the same number of 65536-ray tiles (C4)
+    assert len(D.tiles_for_rank(64 << 20, 3, 8)) == 128
+
+
+def _worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        blob = torch.arange(12345, dtype=torch.int64).to(torch.uint8) if rank == 0 else None
+        blob = D.broadcast_blob(blob, 0, device=torch.device("cpu"))
+        ok_blob = bool(torch.equal(blob, torch.arange(12345, dtype=torch.int64).to(torch.uint8)))
+        n = 1000
+        idx = D.ray_indices_for_rank(n, rank, world, tile=64)
+        local = torch.zeros((len(idx), 6), dtype=torch.int32)
+        local[:, 0] = torch.from_numpy(idx).int()          # "hit" = the global ray index
+        full = D.gather_hits(local, n, 0, tile=64)
+        ok_gather = True if rank != 0 else bool(torch.equal(full[:, 0], torch.arange(n, dtype=torch.int32)))
+        ret[rank] = ok_blob and ok_gather
+    finally:
+        dist.destroy_process_group()
+
+
+def test_broadcast_and_gather_gloo_world2():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret[0] and ret[1]
