@@ -279,8 +279,8 @@ def main():
     d_any = torch.empty(n, dtype=torch.int32, device=tdev)
 
     # ------------------------------------------------------------------ counted pass (instrumented kernel, untimed)
-    ctr_p = torch.zeros(3, dtype=torch.int64, device=tdev)
-    ctr_b = torch.zeros(3, dtype=torch.int64, device=tdev)
+    ctr_p = torch.zeros(4, dtype=torch.int64, device=tdev)
+    ctr_b = torch.zeros(4, dtype=torch.int64, device=tdev)
     acc.trace_closest(d_primary, out=d_hits_p, counters=ctr_p)
     acc.trace_closest(d_bounce, out=d_hits_b, counters=ctr_b)
     torch.cuda.synchronize()

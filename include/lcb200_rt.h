@@ -105,7 +105,8 @@ LCRT_API int lcrtRefitTlas(lcrtStream stream, const void *instances, uint32_t in
 
 /* Batch tracing.  masks: device array of `ray_count` u32 if masks != NULL, else `mask` for every ray.
  * hits: SurfaceHit[ray_count] (miss <=> inst == 0xffffffff).  occluded: u32[ray_count] (0 / 1).
- * counters (optional, device, 3 x u64): += BVH8 nodes visited, primitive records tested, instance leaves entered. */
+ * counters (optional, device, 4 x u64): += BVH8 nodes visited, primitive records tested, instance leaves entered,
+ * double-precision triangle evaluations taken by the fp32 filter's fallback. */
 LCRT_API int lcrtTraceClosest(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count,
                               const uint32_t *masks, uint32_t mask, void *hits, uint64_t *counters);
 LCRT_API int lcrtTraceAny(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count,

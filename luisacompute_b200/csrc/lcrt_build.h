@@ -135,17 +135,20 @@ struct InstInput {
         const Instance in = inst[i];
         const BlobHeader *h = blas_of(in);
         InstanceRecord r;
-        if (!invert_affine(in.affine, r.inv)) {
-            for (int k = 0; k < 12; k++) r.inv[k] = 0.0;
+        memset(&r, 0, sizeof(r));
+        if (!invert_affine(in.affine, r.inv_exact)) {
+            for (int k = 0; k < 12; k++) r.inv_exact[k] = 0.0;
         }
+        for (int k = 0; k < 12; k++) r.inv[k] = (float)r.inv_exact[k];
+        bool identity = true;
+        for (int k = 0; k < 12; k++) identity = identity && in.affine[k] == ((k == 0 || k == 5 || k == 10) ? 1.f : 0.f);
         r.nodes = h ? (uint64_t)(reinterpret_cast<const char *>(h) + h->nodes_offset) : 0ull;
         r.prims = h ? (uint64_t)(reinterpret_cast<const char *>(h) + h->prims_offset) : 0ull;
         r.inst = i;
         r.mask = h ? (in.mask & 0xffu) : 0u;// an unbound instance can never be entered
         const bool opaque = !(in.flags & INSTANCE_FLAG_ENFORCE_ANYHIT);
-        r.flags = (h ? h->kind : KIND_TRIANGLES) | (opaque ? IREC_OPAQUE : 0u);
-        r.pad = 0u;
-        copy_vec16(dst, &r, 8);
+        r.flags = (h ? h->kind : KIND_TRIANGLES) | (opaque ? IREC_OPAQUE : 0u) | (identity ? IREC_IDENTITY : 0u);
+        copy_vec16(dst, &r, 16);
     }
     LCRT_HD static uint32_t record_prim(const char *rec) { return reinterpret_cast<const InstanceRecord *>(rec)->inst; }
 };

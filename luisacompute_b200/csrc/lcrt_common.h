@@ -19,9 +19,11 @@
 #if defined(__CUDACC__)
 #define LCRT_HD __host__ __device__ __forceinline__
 #define LCRT_HD_NOINLINE __host__ __device__
+#define LCRT_HD_COLD __host__ __device__ __noinline__
 #else
 #define LCRT_HD inline
 #define LCRT_HD_NOINLINE inline
+#define LCRT_HD_COLD inline
 #endif
 
 namespace lcrt {
@@ -250,18 +252,24 @@ static_assert(sizeof(BoxRecord) == 32, "BoxRecord must be 32 bytes");
 
 enum BlasKind : uint32_t { KIND_TRIANGLES = 0u, KIND_AABBS = 1u, KIND_INSTANCES = 2u };
 
-struct alignas(16) InstanceRecord {// 128 B: TLAS leaf, everything the traversal needs to enter a BLAS
-    double inv[12];    // world -> object, row-major 3x4, in double: the exact triangle test re-derives the object-space
-                       // ray from the world ray with it, so hit decisions and t do not inherit fp32 transform rounding
+struct alignas(16) InstanceRecord {// 256 B = two 128-byte lines: TLAS leaf, everything the traversal needs to enter a BLAS
+    // ---- hot line (80 B used): all that an instance entry fetches, five 16-byte vectors
+    float inv[12];     // world -> object, row-major 3x4, fp32 (rounded from inv_exact)
     uint64_t nodes;    // device address of the BLAS's Node8 array
     uint64_t prims;    // device address of the BLAS's primitive records
     uint32_t inst;     // index into the 80-byte instance array
     uint32_t mask;     // visibility mask (8 bits)
-    uint32_t flags;    // bits 0..7: BlasKind of the target, bit 8: opaque
+    uint32_t flags;    // bits 0..7: BlasKind of the target, bit 8: opaque, bit 9: the transform is exactly the identity
     uint32_t pad;
+    uint32_t spare[12];
+    // ---- cold line: only the (rare) double-precision fallback of the triangle test reads it
+    double inv_exact[12];// world -> object in double: the fallback re-derives the object-space ray from the world ray
+                         // with it, so its decisions and t do not inherit fp32 transform rounding
+    uint64_t spare2[4];
 };
-static_assert(sizeof(InstanceRecord) == 128, "InstanceRecord must be 128 bytes");
-constexpr uint32_t IREC_KIND_MASK = 0xffu, IREC_OPAQUE = 1u << 8;
+static_assert(sizeof(InstanceRecord) == 256, "InstanceRecord must be 256 bytes");
+constexpr uint32_t INSTANCE_FETCH_BYTES = 80;// algorithmic bytes of one instance entry (roofline)
+constexpr uint32_t IREC_KIND_MASK = 0xffu, IREC_OPAQUE = 1u << 8, IREC_IDENTITY = 1u << 9;
 
 // ------------------------------------------------------------------------------------------ blob header
 // Every BLAS / TLAS lives in ONE caller-provided allocation ("blob"): header, nodes, primitive records, aux.

@@ -211,18 +211,38 @@ __global__ void k_update_handles(Instance *instances, const InstanceHandleUpdate
 // trace kernels
 // =====================================================================================================================
 constexpr int TRACE_BLOCK = 128;
-constexpr int TRACE_SMEM_STACK = 8;   // entries per thread kept in shared memory
-constexpr int TRACE_STEPS = 6;        // traversal steps between refill checks
+constexpr int TRACE_SMEM_STACK = 8;   // stack entries per thread kept in shared memory
 constexpr uint32_t TRACE_BATCH = 128; // rays a warp reserves per atomic
+#ifndef LCRT_REFILL_MIN
+#define LCRT_REFILL_MIN 6             // idle lanes that trigger a warp-cooperative refill
+#endif
 
-struct HybridStack {
-    u2 *smem;// this thread's column: entry i at smem[i * TRACE_BLOCK]
+// Per-thread storage outside the register file (see LocalStore in lcrt_traverse.h): every array is laid out
+// [entry][thread] so that a warp's accesses to one entry are consecutive words / vectors (conflict free).
+struct TraceSmem {
+    u2 stack[TRACE_SMEM_STACK * TRACE_BLOCK];
+    f4 rows[2 * TRACE_BLOCK];
+    uint32_t words[CW_COUNT * TRACE_BLOCK];
+};
+__device__ __forceinline__ TraceSmem *trace_smem() {
+    // dynamic shared memory (sizeof(TraceSmem) at launch): referencing the array directly keeps every access an
+    // LDS / STS (a pointer member would decay to generic loads and stores)
+    extern __shared__ __align__(16) unsigned char lcrt_trace_smem[];
+    return reinterpret_cast<TraceSmem *>(lcrt_trace_smem);
+}
+struct HybridStore {
     u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
     __device__ __forceinline__ void store(int i, u2 v) {
-        if (i < TRACE_SMEM_STACK) smem[i * TRACE_BLOCK] = v;
+        if (i < TRACE_SMEM_STACK) trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] = v;
         else local[i - TRACE_SMEM_STACK] = v;
     }
-    __device__ __forceinline__ u2 load(int i) const { return i < TRACE_SMEM_STACK ? smem[i * TRACE_BLOCK] : local[i - TRACE_SMEM_STACK]; }
+    __device__ __forceinline__ u2 load(int i) const {
+        return i < TRACE_SMEM_STACK ? trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] : local[i - TRACE_SMEM_STACK];
+    }
+    __device__ __forceinline__ void st4(int k, f4 v) { trace_smem()->rows[k * TRACE_BLOCK + threadIdx.x] = v; }
+    __device__ __forceinline__ f4 ld4(int k) const { return trace_smem()->rows[k * TRACE_BLOCK + threadIdx.x]; }
+    __device__ __forceinline__ void stw(int k, uint32_t v) { trace_smem()->words[k * TRACE_BLOCK + threadIdx.x] = v; }
+    __device__ __forceinline__ uint32_t ldw(int k) const { return trace_smem()->words[k * TRACE_BLOCK + threadIdx.x]; }
 };
 
 struct TraceParams {
@@ -237,79 +257,72 @@ struct TraceParams {
     unsigned long long *counters;// optional
     uint32_t tri_prog, proc_prog;
     int terminate_on_first;
+    uint32_t magic;              // PLANT_MAGIC, see plant_byte()
 };
 
+// Persistent threads: every warp reserves TRACE_BATCH consecutive rays per atomic and hands them to its idle lanes
+// (ballot + popc rank) whenever at least LCRT_REFILL_MIN lanes are idle; between refills every lane advances its
+// ray by one step() per iteration.  Surface hits are written in a provisional form (u = TLAS record index, prim =
+// primitive record index, t = fp32 distance) that k_refine_hits turns into the final record.
 template<int MODE, bool COUNT, class Callbacks>
-__global__ void __launch_bounds__(TRACE_BLOCK, 4) k_trace(TraceParams p) {
-    __shared__ u2 sstack[TRACE_SMEM_STACK * TRACE_BLOCK];
-    HybridStack stack;
-    stack.smem = sstack + threadIdx.x;
+__global__ void __launch_bounds__(TRACE_BLOCK, 5) k_trace(TraceParams p) {
+    HybridStore store;
     Callbacks cb;
     if constexpr (MODE == MODE_QUERY) cb = Callbacks{p.tri_prog, p.proc_prog};
-    Traversal<MODE, COUNT, HybridStack, Callbacks> tr;
+    Traversal<MODE, COUNT, HybridStore, Callbacks> tr;
+    tr.done = true;
+    tr.magic = p.magic;
+    const u4 *tlas_nodes = reinterpret_cast<const u4 *>(reinterpret_cast<const char *>(p.tlas) + p.tlas->nodes_offset);
+    const InstanceRecord *tlas_recs = reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(p.tlas) + p.tlas->prims_offset);
+    const bool single = p.tlas->prim_count == 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     bool active = false;
-    uint64_t ray_idx = 0;
     uint64_t warp_next = 0, warp_end = 0;// this warp's reserved range of ray indices
-    unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0;
+    unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0, c_exact = 0;
     bool exhausted = false;
     for (;;) {
         // ---- warp-cooperative refill of idle lanes
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted) {
+        if (idle && !exhausted && ((uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN || idle == 0xffffffffu)) {
             const uint32_t want = (uint32_t)__popc(idle);
-            if (warp_end - warp_next < want) {
-                // keep what is left, reserve a fresh batch when the remainder can not serve all idle lanes
-                if (warp_next == warp_end) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(p.next, (unsigned long long)TRACE_BATCH);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    warp_next = base < p.n ? base : p.n;
-                    warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
-                    if (warp_next == warp_end) exhausted = true;
-                }
+            if (warp_next == warp_end) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(p.next, (unsigned long long)TRACE_BATCH);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                warp_next = base < p.n ? base : p.n;
+                warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
+                if (warp_next == warp_end) exhausted = true;
             }
             const uint64_t avail = warp_end - warp_next;
             const uint32_t rank = (uint32_t)__popc(idle & lt_mask);
             if (!active && rank < avail) {
-                ray_idx = warp_next + rank;
-                const f4 *rp = reinterpret_cast<const f4 *>(p.rays + ray_idx);
-                const f4 r0 = rp[0], r1 = rp[1];
-                Ray ray;
-                ray.ox = r0.x, ray.oy = r0.y, ray.oz = r0.z, ray.tmin = r0.w, ray.dx = r1.x, ray.dy = r1.y, ray.dz = r1.z, ray.tmax = r1.w;
-                tr.init(p.tlas, p.instances, ray, p.masks ? p.masks[ray_idx] : p.mask, &stack, &cb);
+                const uint64_t ray_idx = warp_next + rank;
+                tr.init(tlas_nodes, tlas_recs, single, p.instances, p.rays + ray_idx, p.masks ? p.masks[ray_idx] : p.mask, &store, &cb);
                 if constexpr (MODE == MODE_QUERY) tr.terminate_on_first = p.terminate_on_first != 0;
                 active = true;
             }
             warp_next += want < avail ? want : avail;
+        } else if (idle == 0xffffffffu) {
+            break;
         }
-        if (__ballot_sync(0xffffffffu, active) == 0u) break;
-        // ---- a bounded number of traversal steps
-        if (active) {
-#pragma unroll 1
-            for (int k = 0; k < TRACE_STEPS; k++) {
-                if (!tr.step()) {
-                    if constexpr (MODE == MODE_CLOSEST) {
-                        SurfaceHit h;
-                        const bool hit = tr.hit_inst != ~0u;
-                        h.inst = tr.hit_inst, h.prim = tr.hit_prim, h.u = tr.hit_u, h.v = tr.hit_v;
-                        h.t = hit ? (float)tr.t_best : tr.world.tmax, h.pad = 0u;
-                        u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
-                        o[0] = make_u2(h.inst, h.prim), o[1] = make_u2(as_uint(h.u), as_uint(h.v)), o[2] = make_u2(as_uint(h.t), 0u);
-                    } else if constexpr (MODE == MODE_ANY) {
-                        static_cast<uint32_t *>(p.out)[ray_idx] = tr.hit_inst != ~0u ? 1u : 0u;
-                    } else {
-                        const bool hit = tr.hit_type != HIT_MISS;
-                        u2 *o = reinterpret_cast<u2 *>(static_cast<CommittedHit *>(p.out) + ray_idx);
-                        o[0] = make_u2(tr.hit_inst, tr.hit_prim), o[1] = make_u2(as_uint(tr.hit_u), as_uint(tr.hit_v));
-                        o[2] = make_u2(tr.hit_type, as_uint(hit ? (float)tr.t_best : tr.world.tmax));
-                    }
-                    if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts;
-                    active = false;
-                    break;
-                }
+        // ---- one traversal step per lane
+        if (active && !tr.step()) {
+            const uint64_t ray_idx = (uint64_t)(tr.world - p.rays);
+            const bool hit = tr.has_hit();
+            if constexpr (MODE == MODE_CLOSEST) {
+                u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
+                o[0] = make_u2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u), o[1] = make_u2(hit ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(as_uint(tr.hit_t()), 0u);
+            } else if constexpr (MODE == MODE_ANY) {
+                static_cast<uint32_t *>(p.out)[ray_idx] = hit ? 1u : 0u;
+            } else {
+                const uint32_t type = tr.hit_type();
+                u2 *o = reinterpret_cast<u2 *>(static_cast<CommittedHit *>(p.out) + ray_idx);
+                o[0] = make_u2(tr.hit_inst(), type == HIT_SURFACE ? tr.hit_pi() : tr.hit_prim());
+                o[1] = make_u2(type == HIT_SURFACE ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(type, as_uint(tr.hit_t()));
             }
+            if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts, c_exact += tr.ctr.exact;
+            active = false;
         }
     }
     if constexpr (COUNT) {
@@ -318,12 +331,38 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 4) k_trace(TraceParams p) {
             c_nodes += __shfl_xor_sync(0xffffffffu, c_nodes, o);
             c_prims += __shfl_xor_sync(0xffffffffu, c_prims, o);
             c_insts += __shfl_xor_sync(0xffffffffu, c_insts, o);
+            c_exact += __shfl_xor_sync(0xffffffffu, c_exact, o);
         }
         if (lane == 0 && p.counters) {
             atomicAdd(&p.counters[0], c_nodes);
             atomicAdd(&p.counters[1], c_prims);
             atomicAdd(&p.counters[2], c_insts);
+            atomicAdd(&p.counters[3], c_exact);
         }
+    }
+}
+
+// Second pass of closest-hit / RayQuery batches: the reported (t, u, v) of every surface hit are recomputed in
+// double with the oracle's formula (refine_surface_hit), one thread per ray, fully convergent and coalesced.
+template<int MODE>
+__global__ void __launch_bounds__(256) k_refine_hits(const BlobHeader *tlas, const Ray *__restrict__ rays, void *out, uint64_t n) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const InstanceRecord *tlas_recs = reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(tlas) + tlas->prims_offset);
+    u2 *o = reinterpret_cast<u2 *>(static_cast<char *>(out) + i * 24u);
+    const u2 h0 = o[0], h1 = o[1], h2 = o[2];
+    if constexpr (MODE == MODE_CLOSEST) {
+        if (h0.x == ~0u) return;
+        uint32_t prim = 0;
+        float t = as_float(h2.x), u = 0.f, v = 0.f;
+        refine_surface_hit(rays + i, tlas_recs, h1.x, h0.y, prim, t, u, v);
+        o[0] = make_u2(h0.x, prim), o[1] = make_u2(as_uint(u), as_uint(v)), o[2] = make_u2(as_uint(t), 0u);
+    } else {
+        if (h2.x != HIT_SURFACE) return;
+        uint32_t prim = 0;
+        float t = as_float(h2.y), u = 0.f, v = 0.f;
+        refine_surface_hit(rays + i, tlas_recs, h1.x, h0.y, prim, t, u, v);
+        o[0] = make_u2(h0.x, prim), o[1] = make_u2(as_uint(u), as_uint(v)), o[2] = make_u2(HIT_SURFACE, as_uint(t));
     }
 }
 
@@ -484,21 +523,25 @@ static int trace_generic(cudaStream_t stream, const void *tlas, const void *inst
     p.rays = static_cast<const Ray *>(rays), p.n = n, p.masks = masks, p.mask = mask, p.out = out;
     p.next = dev->cursors + (g_cursor_next.fetch_add(1) % CURSOR_RING);
     p.counters = reinterpret_cast<unsigned long long *>(counters);
-    p.tri_prog = tri_prog, p.proc_prog = proc_prog, p.terminate_on_first = terminate_on_first;
+    p.tri_prog = tri_prog, p.proc_prog = proc_prog, p.terminate_on_first = terminate_on_first, p.magic = PLANT_MAGIC;
     LCRT_CUDA(cudaMemsetAsync(p.next, 0, sizeof(unsigned long long), stream));
     int bps = 0;
     if (counters) {
-        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, true, Callbacks>, TRACE_BLOCK, 0));
+        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, true, Callbacks>, TRACE_BLOCK, sizeof(TraceSmem)));
     } else {
-        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, false, Callbacks>, TRACE_BLOCK, 0));
+        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, false, Callbacks>, TRACE_BLOCK, sizeof(TraceSmem)));
     }
     if (bps < 1) bps = 1;
     uint64_t g = (uint64_t)dev->sm_count * (uint64_t)bps;
     const uint64_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
     if (g > need) g = need;
-    if (counters) k_trace<MODE, true, Callbacks><<<(uint32_t)g, TRACE_BLOCK, 0, stream>>>(p);
-    else k_trace<MODE, false, Callbacks><<<(uint32_t)g, TRACE_BLOCK, 0, stream>>>(p);
+    if (counters) k_trace<MODE, true, Callbacks><<<(uint32_t)g, TRACE_BLOCK, sizeof(TraceSmem), stream>>>(p);
+    else k_trace<MODE, false, Callbacks><<<(uint32_t)g, TRACE_BLOCK, sizeof(TraceSmem), stream>>>(p);
     LCRT_LAUNCH_CHECK("k_trace");
+    if (MODE != MODE_ANY) {
+        k_refine_hits<MODE><<<(uint32_t)((n + 255u) / 256u), 256, 0, stream>>>(p.tlas, p.rays, out, n);
+        LCRT_LAUNCH_CHECK("k_refine_hits");
+    }
     return LCRT_SUCCESS;
 }
 

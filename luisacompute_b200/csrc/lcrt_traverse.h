@@ -6,12 +6,27 @@
 // `mask & 0xff` against the instance mask, no face culling, procedural primitives invisible) and :1896-1967
 // (query_all / query_any).
 //
-// Algorithm: compressed-wide-BVH traversal (Ylitie et al. 2017): a node group = (child base, hit bits | imask),
-// a primitive group = (prim base, hit bits); octant-ordered child visiting via `slot ^ octinv`; per-thread stack.
-// Box tests are fp32 and conservative (never stricter than exact arithmetic); the triangle test is a conservative
-// fp32 edge-function prefilter followed by a double-precision evaluation that decides the hit and produces
-// (t, u, v).  Edge functions are evaluated as non-contracted scalar triple products d.(B x C), which are exactly
-// antisymmetric under exchanging the two vertices of a shared edge => watertight.
+// Algorithm: compressed-wide-BVH traversal (Ylitie et al. 2017).  A node group = (child base, hit bits | imask), a
+// primitive group = (node index, hit leaf slots); octant-ordered child visiting via `slot ^ octinv`; per-thread stack.
+// One step() = at most one node test followed by at most one primitive test, so lanes of a warp that are in
+// different phases of their rays share both code blocks.
+//
+// Arithmetic, tuned to the measured sm_100a issue costs (tools/ubench_alu.cu: FFMA/FMNMX/FSETP 1 cycle per warp
+// instruction, LOP3/PRMT/SHF/SEL 2, I2F.U8/FLO/POPC 8):
+//   * box test: the quantised plane byte is planted into the mantissa of 2^23 by ONE PRMT (val = 2^23 + 256 q) and
+//     the plane distance is ONE FFMA val * a' + b' with the 2^23 offset folded into b'; no integer-to-float
+//     conversion, no per-child bit arithmetic (the node test returns an 8-bit slot mask).  Conservative: the
+//     (a', b') pairs are widened so that the near (far) distance is a lower (upper) bound of the exact one.
+//   * triangle test: fp32 edge functions in a ray-aligned sheared frame (after Woop, Benthin, Wald 2013) with an
+//     explicit forward error bound.  A decision is taken in fp32 only when every edge function clears its bound;
+//     the fp32 distance comes with its own error bound and candidates are ordered by interval comparison.  Whatever
+//     fp32 can not decide (ray within rounding of an edge, two surfaces within rounding of each other, t within
+//     rounding of the ray's interval ends) is re-evaluated by tri_exact_world() in double precision with the
+//     oracle's formula (non-contracted scalar triple products, exactly antisymmetric under exchanging the two
+//     vertices of a shared edge => watertight).  Decisions therefore equal those of an all-double evaluation.
+//   * the reported (t, u, v) of the winning triangle are always recomputed in double (refine_hit): fp32 can not
+//     deliver 1e-4 barycentrics for a 4 mm triangle seen from 2 m.  The batch kernels do that in a separate,
+//     fully convergent pass over the hit records (k_refine_hits); the inline entry points do it at the end.
 #pragma once
 #include "lcrt_common.h"
 
@@ -22,7 +37,7 @@ namespace lcrt {
 #endif
 
 struct TraceCounters {
-    uint32_t nodes, prims, insts;
+    uint32_t nodes, prims, insts, exact;
 };
 
 enum TraceMode : int { MODE_CLOSEST = 0, MODE_ANY = 1, MODE_QUERY = 2 };
@@ -40,86 +55,184 @@ struct NoCallbacks {
     LCRT_HD CandidateResult on_procedural(uint32_t, uint32_t, const Ray &, const Instance *, const f4, const f4) const { return {0.f, false, false}; }
 };
 
-// Simple local-memory stack (inline device-library path and host simulation).
-struct LocalStack {
+// Per-ray storage outside the register file: the traversal stack plus the "cold" ray state that is touched once per
+// primitive test or once per accepted hit.  The batch kernel keeps the first stack entries and all cold state in
+// shared memory (lcrt_kernels.cu HybridStore); this plain version serves the host simulation and the inline
+// device-library entry points.
+enum ColdWord : int {
+    CW_SZ = 0,    // 1 / d_kz of the current-space direction
+    CW_KZ,        // dominant axis of the current-space direction
+    CW_REC,       // TLAS record index of the instance being traversed
+    CW_HIT_T,     // best accepted t (fp32)
+    CW_HIT_TERR,  // its absolute error bound; < 0: no hit yet (CW_HIT_T is then the ray's tmax, exact)
+    CW_HIT_REC,   // TLAS record index of the best hit
+    CW_HIT_PI,    // primitive record index of the best hit inside its BLAS
+    CW_HIT_INST,  // instance / primitive ids of the best hit (tie-breaks)
+    CW_HIT_PRIM,
+    CW_HIT_TYPE,
+    CW_HIT_TD_LO, // exact t of the best hit as a double, valid iff CW_HIT_EXACT
+    CW_HIT_TD_HI,
+    CW_HIT_EXACT,
+    CW_COUNT
+};
+struct LocalStore {
     u2 e[LCRT_STACK_SIZE];
+    f4 rows[2];
+    uint32_t words[CW_COUNT];
     LCRT_HD void store(int i, u2 v) { e[i] = v; }
     LCRT_HD u2 load(int i) const { return e[i]; }
+    LCRT_HD void st4(int k, f4 v) { rows[k] = v; }
+    LCRT_HD f4 ld4(int k) const { return rows[k]; }
+    LCRT_HD void stw(int k, uint32_t v) { words[k] = v; }
+    LCRT_HD uint32_t ldw(int k) const { return words[k]; }
 };
 
 LCRT_HD float safe_dir(float d) {
-    // avoid 0 * inf in the slab test; 1e-20 keeps 255 * 2^e * idir finite for any sane scene
+    // avoid 0 * inf in the slab test; 1e-20 keeps 2^15 * 255 * 2^e * idir finite for any sane scene
     return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
 }
 
+// 16-byte read-only loads of BVH data (never written while a trace is in flight)
+template<class T>
+LCRT_HD T ldg16(const T *p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+
+// float whose mantissa carries byte `j` of `w` in bits 8..15: 2^23 + 256 * byte
+// `magic` must hold PLANT_MAGIC; it is passed in (from a kernel parameter) so that it lives in a uniform register and
+// the selector can be the instruction's immediate — as a literal, ptxas makes it the immediate and re-materialises
+// the selector into a register for every PRMT.
+constexpr uint32_t PLANT_MAGIC = 0x4B000000u;
+template<int J>
+LCRT_HD float plant_byte(uint32_t w, uint32_t magic) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(magic), "n"(0x7604 | (J << 4)));
+    return __uint_as_float(r);
+#else
+    return as_float(magic | (((w >> (8 * J)) & 0xffu) << 8));
+#endif
+}
+
 // --------------------------------------------------------------------------------------------------------------
-// Node test: returns the hit bits (top byte: internal children by traversal priority, low 24: primitives)
+// Node test: returns the 8-bit mask of child slots whose (conservatively widened) box the ray interval overlaps.
+// Empty slots are stored inverted (lo 255, hi 0) and fail unless the node is degenerate; callers mask the result
+// with imask (internal children) or check meta != 0 (leaf slots).
 // --------------------------------------------------------------------------------------------------------------
-LCRT_HD uint32_t intersect_node8(const u4 n0, const u4 n1, const u4 n2, const u4 n3, const u4 n4, float ox, float oy, float oz,
-                                 float idx, float idy, float idz, float tmin, float tmax, uint32_t octinv4) {
-    const float sx = as_float((n0.w & 0xffu) << 23), sy = as_float(((n0.w >> 8) & 0xffu) << 23),
-                sz = as_float(((n0.w >> 16) & 0xffu) << 23);
-    // t = q * a + b; (a, b) widened by K so that the near (far) distance is a lower (upper) bound of the exact one
+struct AxisCoef {
+    float an, bn, af, bf;// t_near(q) >= val(q) * an + bn ; t_far(q) <= val(q) * af + bf
+};
+LCRT_HD AxisCoef axis_coef(uint32_t ebyte, float p, float o, float id) {
+    // exact: t(q) = q * a + b, a = 2^(e-127) / d, b = (p - o) / d.  Rounding of (1/d, p - o, the products, the final
+    // FFMA) is covered by widening a and b by K = 10 ulp relative (as before); planting q as 2^23 + 256 q turns the
+    // FFMA into val * (a / 256) + (b - 2^15 a), whose extra cancellation error (<= 2^15 |a| * 2^-24 = |a| / 512 per
+    // rounding) is covered by a slack of |a| / 128, i.e. less than 1 % of one quantisation step.
     constexpr float K = 6.0e-7f;
-    const float ax = sx * idx, ay = sy * idy, az = sz * idz;
-    const float bx = (as_float(n0.x) - ox) * idx, by = (as_float(n0.y) - oy) * idy, bz = (as_float(n0.z) - oz) * idz;
-    const float axn = fmaf(-K, fabsf(ax), ax), ayn = fmaf(-K, fabsf(ay), ay), azn = fmaf(-K, fabsf(az), az);
-    const float axf = fmaf(K, fabsf(ax), ax), ayf = fmaf(K, fabsf(ay), ay), azf = fmaf(K, fabsf(az), az);
-    const float bxn = fmaf(-K, fabsf(bx), bx), byn = fmaf(-K, fabsf(by), by), bzn = fmaf(-K, fabsf(bz), bz);
-    const float bxf = fmaf(K, fabsf(bx), bx), byf = fmaf(K, fabsf(by), by), bzf = fmaf(K, fabsf(bz), bz);
-    uint32_t hitmask = 0u;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int i = 0; i < 2; i++) {
-        const uint32_t meta4 = i ? n1.w : n1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
-        const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t qlox = i ? n2.y : n2.x, qloy = i ? n2.w : n2.z, qloz = i ? n3.y : n3.x;
-        const uint32_t qhix = i ? n3.w : n3.z, qhiy = i ? n4.y : n4.x, qhiz = i ? n4.w : n4.z;
-        const uint32_t nx = idx < 0.f ? qhix : qlox, fx = idx < 0.f ? qlox : qhix;
-        const uint32_t ny = idy < 0.f ? qhiy : qloy, fy = idy < 0.f ? qloy : qhiy;
-        const uint32_t nz = idz < 0.f ? qhiz : qloz, fz = idz < 0.f ? qloz : qhiz;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; j++) {
-            const float tnx = fmaf((float)extract_byte(nx, j), axn, bxn);
-            const float tny = fmaf((float)extract_byte(ny, j), ayn, byn);
-            const float tnz = fmaf((float)extract_byte(nz, j), azn, bzn);
-            const float tfx = fmaf((float)extract_byte(fx, j), axf, bxf);
-            const float tfy = fmaf((float)extract_byte(fy, j), ayf, byf);
-            const float tfz = fmaf((float)extract_byte(fz, j), azf, bzf);
-            const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-            const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-            if (tn <= tf) hitmask |= extract_byte(child_bits4, j) << extract_byte(bit_index4, j);
-        }
+    const float s = as_float(ebyte << 23);
+    const float a256 = (s * id) * (1.0f / 256.0f);
+    const float b = (p - o) * id;
+    AxisCoef c;
+    c.an = fmaf(-K, fabsf(a256), a256);
+    c.af = fmaf(K, fabsf(a256), a256);
+    c.bn = fmaf(-2.0f, fabsf(a256), fmaf(-8388608.0f, c.an, fmaf(-K, fabsf(b), b)));
+    c.bf = fmaf(2.0f, fabsf(a256), fmaf(-8388608.0f, c.af, fmaf(K, fabsf(b), b)));
+    return c;
+}
+
+LCRT_HD uint32_t intersect_node8(const u4 n0, const u4 n2, const u4 n3, const u4 n4, float ox, float oy, float oz, float idx, float idy,
+                                 float idz, float tmin, float tmax, uint32_t magic) {
+    const AxisCoef cx = axis_coef(n0.w & 0xffu, as_float(n0.x), ox, idx);
+    const AxisCoef cy = axis_coef((n0.w >> 8) & 0xffu, as_float(n0.y), oy, idy);
+    const AxisCoef cz = axis_coef((n0.w >> 16) & 0xffu, as_float(n0.z), oz, idz);
+    uint32_t hm = 0u;
+#define LCRT_CHILD(J, SLOT)                                                                                \
+    {                                                                                                      \
+        const float tnx = fmaf(plant_byte<J>(nx, magic), cx.an, cx.bn), tfx = fmaf(plant_byte<J>(fx, magic), cx.af, cx.bf); \
+        const float tny = fmaf(plant_byte<J>(ny, magic), cy.an, cy.bn), tfy = fmaf(plant_byte<J>(fy, magic), cy.af, cy.bf); \
+        const float tnz = fmaf(plant_byte<J>(nz, magic), cz.an, cz.bn), tfz = fmaf(plant_byte<J>(fz, magic), cz.af, cz.bf); \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                         \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                         \
+        if (tn <= tf) hm += 1u << (SLOT);                                                                  \
     }
-    return hitmask;
+    {
+        const uint32_t nx = idx < 0.f ? n3.z : n2.x, fx = idx < 0.f ? n2.x : n3.z;
+        const uint32_t ny = idy < 0.f ? n4.x : n2.z, fy = idy < 0.f ? n2.z : n4.x;
+        const uint32_t nz = idz < 0.f ? n4.z : n3.x, fz = idz < 0.f ? n3.x : n4.z;
+        LCRT_CHILD(0, 0) LCRT_CHILD(1, 1) LCRT_CHILD(2, 2) LCRT_CHILD(3, 3)
+    }
+    {
+        const uint32_t nx = idx < 0.f ? n3.w : n2.y, fx = idx < 0.f ? n2.y : n3.w;
+        const uint32_t ny = idy < 0.f ? n4.y : n2.w, fy = idy < 0.f ? n2.w : n4.y;
+        const uint32_t nz = idz < 0.f ? n4.w : n3.y, fz = idz < 0.f ? n3.y : n4.w;
+        LCRT_CHILD(0, 4) LCRT_CHILD(1, 5) LCRT_CHILD(2, 6) LCRT_CHILD(3, 7)
+    }
+#undef LCRT_CHILD
+    return hm;
+}
+
+// permute the 8 slot bits by slot -> slot ^ k (k = 7 - octant): the traversal visits the highest set bit first
+LCRT_HD uint32_t permute_slots(uint32_t m, uint32_t k) {
+    if (k & 1u) m = ((m & 0x55u) << 1) | ((m >> 1) & 0x55u);
+    if (k & 2u) m = ((m & 0x33u) << 2) | ((m >> 2) & 0x33u);
+    if (k & 4u) m = ((m & 0x0fu) << 4) | ((m >> 4) & 0x0fu);
+    return m;
 }
 
 // --------------------------------------------------------------------------------------------------------------
 // Triangle test
 // --------------------------------------------------------------------------------------------------------------
-// fp32 conservative prefilter: false => the ray certainly misses (in exact arithmetic).
-// `oerr`: absolute error bound of the (fp32, possibly instance-transformed) ray origin.
-LCRT_HD bool tri_prefilter(float ox, float oy, float oz, float dx, float dy, float dz, float oerr, const f4 v0, const f4 v1, const f4 v2) {
+constexpr float LCRT_U = 5.9604645e-8f;// 2^-24: unit roundoff of fp32 (round to nearest)
+
+enum TriVerdict : int { TRI_MISS = 0, TRI_HIT = 1, TRI_UNSURE = 2 };
+
+// fp32 test in the sheared frame.  r1 / r2 are the rows of the shear (entries 1, 0 and -d_kx/d_kz resp. -d_ky/d_kz
+// with kz the dominant axis of d), so (A.r1, A.r2) are the coordinates of A in the plane z' = 0 of a frame whose z'
+// axis is the ray; the 2D edge functions equal the exact scalar triple products d.(B x C) / d_kz.
+//   r1.w = 2 * (absolute error bound of the fp32 ray origin, 0 for untransformed rays)
+//   r2.w = 3 u + (error bound of the shear entries beyond their own rounding, 0 for untransformed rays)
+// Error model (DESIGN.md "triangle test"): with bm the largest |component| of the ray-relative vertices and m2 the
+// largest |2D coordinate|, every 2D coordinate is within e = bm * r2.w + r1.w + u * m2 of its exact value
+// (subtraction, shear product, shear entry, FFMA rounding), an edge function within 4 e m2 + 2 e^2 + 4 u m2^2.
+// The bound E carries 25 % head room.  TRI_HIT: all three edge functions exceed E with the same sign; TRI_MISS: two
+// of them provably differ in sign; everything else (including NaN) is TRI_UNSURE.  For TRI_HIT, t is the fp32
+// distance and terr a bound of |t - t_exact|.
+LCRT_HD int tri_test_f32(float ox, float oy, float oz, const f4 r1, const f4 r2, float sz, uint32_t kz, const f4 v0, const f4 v1,
+                         const f4 v2, float &t, float &terr) {
+    const float oerr2 = r1.w, cerr = r2.w;
     const float Ax = v0.x - ox, Ay = v0.y - oy, Az = v0.z - oz;
     const float Bx = v1.x - ox, By = v1.y - oy, Bz = v1.z - oz;
     const float Cx = v2.x - ox, Cy = v2.y - oy, Cz = v2.z - oz;
-    const float U = dx * (By * Cz - Bz * Cy) + dy * (Bz * Cx - Bx * Cz) + dz * (Bx * Cy - By * Cx);
-    const float V = dx * (Cy * Az - Cz * Ay) + dy * (Cz * Ax - Cx * Az) + dz * (Cx * Ay - Cy * Ax);
-    const float W = dx * (Ay * Bz - Az * By) + dy * (Az * Bx - Ax * Bz) + dz * (Ax * By - Ay * Bx);
+    const float ax = fmaf(Az, r1.z, fmaf(Ay, r1.y, mul_rn(Ax, r1.x))), ay = fmaf(Az, r2.z, fmaf(Ay, r2.y, mul_rn(Ax, r2.x)));
+    const float bx = fmaf(Bz, r1.z, fmaf(By, r1.y, mul_rn(Bx, r1.x))), by = fmaf(Bz, r2.z, fmaf(By, r2.y, mul_rn(Bx, r2.x)));
+    const float cx = fmaf(Cz, r1.z, fmaf(Cy, r1.y, mul_rn(Cx, r1.x))), cy = fmaf(Cz, r2.z, fmaf(Cy, r2.y, mul_rn(Cx, r2.x)));
+    const float U = fmaf(cx, by, -mul_rn(cy, bx));
+    const float V = fmaf(ax, cy, -mul_rn(ay, cx));
+    const float W = fmaf(bx, ay, -mul_rn(by, ax));
     const float bm = fmaxf(fmaxf(fmaxf(fabsf(Ax), fabsf(Ay)), fmaxf(fabsf(Az), fabsf(Bx))),
                            fmaxf(fmaxf(fmaxf(fabsf(By), fabsf(Bz)), fmaxf(fabsf(Cx), fabsf(Cy))), fabsf(Cz)));
-    const float dm = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-    // |fl(U) - U| <= ~12 eps * dm * bm^2 (three products of three factors, two levels of sums); use 32 eps
-    const float E = dm * bm * fmaf(3.9e-6f, bm, 12.f * oerr);
-    const bool neg = (U < -E) | (V < -E) | (W < -E);
-    const bool pos = (U > E) | (V > E) | (W > E);
-    return !(neg & pos);
+    const float m2 = fmaxf(fmaxf(fmaxf(fabsf(ax), fabsf(ay)), fmaxf(fabsf(bx), fabsf(by))), fmaxf(fabsf(cx), fabsf(cy)));
+    const float e = fmaf(bm, cerr, fmaf(LCRT_U, m2, oerr2));
+    const float E = fmaf(m2, fmaf(5.0f * LCRT_U, m2, 5.0f * e), 2.5f * e * e);
+    const bool pu = U > E, pv = V > E, pw = W > E, nu = U < -E, nv = V < -E, nw = W < -E;
+    if ((pu | pv | pw) & (nu | nv | nw)) return TRI_MISS;
+    if (!((pu & pv & pw) | (nu & nv & nw))) return TRI_UNSURE;
+    // ---- certainly inside: t = sum b_i z_i with z_i the vertex distances along the ray
+    const float det = U + V + W;
+    const float za = (kz == 0u ? Ax : kz == 1u ? Ay : Az) * sz, zb = (kz == 0u ? Bx : kz == 1u ? By : Bz) * sz,
+                zc = (kz == 0u ? Cx : kz == 1u ? Cy : Cz) * sz;
+    const float T = fmaf(U, za, fmaf(V, zb, W * zc));
+    const float rdet = 1.0f / det;
+    t = T * rdet;
+    // |b_i - b_i_exact| <= 4 E / |det| and the errors sum to zero, so they move t by at most 6 (E / |det|) zspread;
+    // the z_i are within (r2.w + 3 u) zmax + |sz| oerr of exact; the accumulation and the division add 6 u zmax.
+    const float zmax = fmaxf(fabsf(za), fmaxf(fabsf(zb), fabsf(zc)));
+    const float zspread = fmaxf(za, fmaxf(zb, zc)) - fminf(za, fminf(zb, zc));
+    terr = 1.25f * fmaf(6.0f * E * fabsf(rdet), zspread, fmaf(cerr + 9.0f * LCRT_U, zmax, fabsf(sz) * oerr2));
+    return terr == terr ? TRI_HIT : TRI_UNSURE;
 }
 
 // Double-precision evaluation: decides the hit exactly like the oracle's formula (oracle/oracle.cpp tri_hit).
@@ -161,6 +274,24 @@ LCRT_HD bool tri_exact(double ox, double oy, double oz, double dx, double dy, do
     return true;
 }
 
+// The fallback: object-space ray re-derived in double from the world ray and the instance's double inverse, then
+// tri_exact.  Out of line on the device so that its registers do not weigh on the traversal loop.
+LCRT_HD_COLD bool tri_exact_world(const Ray *world, const InstanceRecord *rec, const f4 *tri, double &t, float &u, float &v) {
+    const f4 v0 = tri[0], v1 = tri[1], v2 = tri[2];
+    const double wox = world->ox, woy = world->oy, woz = world->oz, wdx = world->dx, wdy = world->dy, wdz = world->dz;
+    double eox = wox, eoy = woy, eoz = woz, edx = wdx, edy = wdy, edz = wdz;
+    if (!(rec->flags & IREC_IDENTITY)) {
+        const double *m = rec->inv_exact;
+        eox = m[0] * wox + m[1] * woy + m[2] * woz + m[3], eoy = m[4] * wox + m[5] * woy + m[6] * woz + m[7],
+        eoz = m[8] * wox + m[9] * woy + m[10] * woz + m[11];
+        edx = m[0] * wdx + m[1] * wdy + m[2] * wdz, edy = m[4] * wdx + m[5] * wdy + m[6] * wdz, edz = m[8] * wdx + m[9] * wdy + m[10] * wdz;
+    }
+    double ud, vd;
+    if (!tri_exact(eox, eoy, eoz, edx, edy, edz, v0, v1, v2, t, ud, vd)) return false;
+    u = (float)ud, v = (float)vd;
+    return true;
+}
+
 // conservative fp32 slab test against an explicit box (procedural primitives)
 LCRT_HD bool slab_conservative(float lox, float loy, float loz, float hix, float hiy, float hiz, float ox, float oy, float oz, float idx,
                                float idy, float idz, float tmin, float tmax) {
@@ -177,222 +308,357 @@ LCRT_HD bool slab_conservative(float lox, float loy, float loz, float hix, float
     return tn <= tf;
 }
 
+// Exact (t, u, v) and primitive id of an accepted surface hit, given where it was found: TLAS record `rec`,
+// primitive record `pi` of that instance's BLAS.  Returns false if the double evaluation does not confirm the hit
+// (can not happen while the fp32 error bounds hold; callers then keep the fp32 distance).
+LCRT_HD bool refine_surface_hit(const Ray *world, const InstanceRecord *tlas_recs, uint32_t rec, uint32_t pi, uint32_t &prim, float &t,
+                                float &u, float &v) {
+    const InstanceRecord *r = tlas_recs + rec;
+    const f4 *tr = reinterpret_cast<const f4 *>(reinterpret_cast<const char *>(r->prims) + (uint64_t)pi * sizeof(TriRecord));
+    prim = as_uint(tr[0].w);
+    double td;
+    if (!tri_exact_world(world, r, tr, td, u, v)) return false;
+    t = (float)td;
+    return true;
+}
+
 // --------------------------------------------------------------------------------------------------------------
-// Traversal state machine.  `step()` performs one outer iteration (one node, then the primitives it exposed);
+// Traversal state machine.  `step()` performs one outer iteration (at most one node, then at most one primitive);
 // the persistent batch kernel interleaves step() with warp-cooperative ray refetch, the inline device-library
 // entry points simply loop until done.
 // --------------------------------------------------------------------------------------------------------------
-template<int MODE, bool COUNT, class Stack, class Callbacks>
+template<int MODE, bool COUNT, class Store, class Callbacks>
 struct Traversal {
-    // current-space ray
-    float ox, oy, oz, dx, dy, dz, idx, idy, idz;
+    // ---- hot state (registers)
+    float ox, oy, oz, idx, idy, idz;// current-space ray (box tests)
     float tmin;
-    float tmax;   // fp32 upper bound of t_best (rounded up), used for box culling
-    double t_best;// exact comparison value
-    uint32_t octinv4;
-    // level state
+    float tmax;        // culling bound: upper end of the best hit's t interval (CW_HIT_T / CW_HIT_TERR)
+    uint32_t octinv;   // 7 - octant of the current-space direction
     const u4 *nodes;
     const char *prims;
+    u2 G;              // node group: x = child base, y = hit internal children (by priority) << 24 | imask
+    u2 Gt;             // primitive group: x = node index, y = pending leaf slots | remaining prims of the current slot << 8
+    uint32_t tp;       // next primitive record of the current slot
+    int sp, blas_sp;   // blas_sp < 0: traversing the TLAS
+    uint32_t cur_inst, cur_flags, ray_mask;
+    bool done;
+    // ---- level-independent
+    const Ray *world;  // the ray as given (re-read on instance exit, by the fallback and by the RayQuery callbacks)
     const u4 *tlas_nodes;
     const InstanceRecord *tlas_recs;
-    u2 G, Gt;
-    int sp, blas_sp;// blas_sp < 0: traversing the TLAS
-    uint32_t cur_inst, cur_flags, ray_mask;
-    const InstanceRecord *cur_rec;
-    float oerr;// error bound of the object-space origin (fp32 transform), widens the triangle prefilter
-    // result
-    uint32_t hit_inst, hit_prim, hit_type;
-    float hit_u, hit_v;
-    bool done;
-    Ray world;// kept for instance exit and for the RayQuery callbacks
     const Instance *instances;
-    Stack *stack;
+    Store *store;
     Callbacks *cb;
     TraceCounters ctr;
+    bool terminate_on_first = false;// query_any
+    uint32_t magic = PLANT_MAGIC;   // see plant_byte(); the batch kernel overwrites it with the same value from a kernel parameter
+    static constexpr uint32_t RAY_PENDING = 0xffffffffu;// octinv value: the current-space ray must be (re)derived
+    LCRT_HD bool MODE_ANY_QUERY() const { return MODE == MODE_QUERY && terminate_on_first; }
 
-    LCRT_HD void set_ray(float ox_, float oy_, float oz_, float dx_, float dy_, float dz_) {
-        ox = ox_, oy = oy_, oz = oz_, dx = dx_, dy = dy_, dz = dz_;
-        const float sdx = safe_dir(dx_), sdy = safe_dir(dy_), sdz = safe_dir(dz_);
+    // oerr: bound of |o - o_exact| per component; derr: likewise for d (both 0 for the untransformed ray)
+    LCRT_HD void set_ray(float ox_, float oy_, float oz_, float dx, float dy, float dz, float oerr, float derr) {
+        ox = ox_, oy = oy_, oz = oz_;
+        const float sdx = safe_dir(dx), sdy = safe_dir(dy), sdz = safe_dir(dz);
         idx = 1.0f / sdx, idy = 1.0f / sdy, idz = 1.0f / sdz;
         const uint32_t oct = (sdx < 0.f ? 1u : 0u) | (sdy < 0.f ? 2u : 0u) | (sdz < 0.f ? 4u : 0u);
-        octinv4 = (7u - oct) * 0x01010101u;
+        octinv = 7u - oct;
+        // shear rows for the triangle test: kz = dominant axis, (kx, ky, kz) cyclic
+        const float adx = fabsf(dx), ady = fabsf(dy), adz = fabsf(dz);
+        const uint32_t kz = (adx >= ady && adx >= adz) ? 0u : (ady >= adz ? 1u : 2u);
+        const float dk = kz == 0u ? dx : kz == 1u ? dy : dz;
+        const float dkx = kz == 0u ? dy : kz == 1u ? dz : dx;
+        const float dky = kz == 0u ? dz : kz == 1u ? dx : dy;
+        const float nsx = -(dkx / dk), nsy = -(dky / dk);// NaN for a null direction: every test becomes TRI_UNSURE
+        f4 r1, r2;
+        if (kz == 0u) r1 = make_f4(nsx, 1.f, 0.f, 0.f), r2 = make_f4(nsy, 0.f, 1.f, 0.f);
+        else if (kz == 1u) r1 = make_f4(0.f, nsx, 1.f, 0.f), r2 = make_f4(1.f, nsy, 0.f, 0.f);
+        else r1 = make_f4(1.f, 0.f, nsx, 0.f), r2 = make_f4(0.f, 1.f, nsy, 0.f);
+        r1.w = 2.0f * oerr;
+        r2.w = 3.0f * LCRT_U + 2.5f * derr / fabsf(dk);
+        store->st4(0, r1), store->st4(1, r2);
+        store->stw(CW_SZ, as_uint(1.0f / dk)), store->stw(CW_KZ, kz);
     }
 
-    LCRT_HD void init(const BlobHeader *tlas, const Instance *instances_, const Ray &ray, uint32_t mask, Stack *stack_, Callbacks *cb_) {
+    // `single`: the TLAS holds exactly one instance (record 0): its root node is skipped
+    LCRT_HD void init(const u4 *tlas_nodes_, const InstanceRecord *tlas_recs_, bool single, const Instance *instances_, const Ray *ray,
+                      uint32_t mask, Store *store_, Callbacks *cb_) {
         world = ray;
         instances = instances_;
-        stack = stack_, cb = cb_;
-        tlas_nodes = reinterpret_cast<const u4 *>(reinterpret_cast<const char *>(tlas) + tlas->nodes_offset);
-        tlas_recs = reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(tlas) + tlas->prims_offset);
+        store = store_, cb = cb_;
+        tlas_nodes = tlas_nodes_, tlas_recs = tlas_recs_;
         nodes = tlas_nodes, prims = reinterpret_cast<const char *>(tlas_recs);
-        set_ray(ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz);
-        tmin = ray.tmin, tmax = ray.tmax, t_best = (double)ray.tmax;
+        const float tmin_ = ldg16(reinterpret_cast<const f4 *>(ray)).w, tmax_ = ldg16(reinterpret_cast<const f4 *>(ray) + 1).w;
+        tmin = tmin_, tmax = tmax_;
+        // the current-space ray is set up by the first step() that needs it (a single-instance TLAS goes straight to
+        // its instance and never needs the world-space setup)
+        ox = oy = oz = idx = idy = idz = 0.f;
+        octinv = single ? 0u : RAY_PENDING;
         ray_mask = mask & 0xffu;
-        G = make_u2(0u, 0x80000000u), Gt = make_u2(0u, 0u);
+        G = single ? make_u2(0u, 0u) : make_u2(0u, 0x80000000u);
+        Gt = single ? make_u2(0u, 1u << 8) : make_u2(0u, 0u);
+        tp = 0u;
         sp = 0, blas_sp = -1;
-        cur_inst = ~0u, cur_flags = 0u, cur_rec = nullptr, oerr = 0.f;
-        hit_inst = ~0u, hit_prim = ~0u, hit_type = HIT_MISS, hit_u = 0.f, hit_v = 0.f;
-        ctr.nodes = ctr.prims = ctr.insts = 0u;
+        cur_inst = ~0u, cur_flags = 0u;
+        store->stw(CW_HIT_T, as_uint(tmax_)), store->stw(CW_HIT_TERR, as_uint(-1.0f));
+        store->stw(CW_HIT_INST, ~0u), store->stw(CW_HIT_PRIM, ~0u), store->stw(CW_HIT_TYPE, HIT_MISS);
+        store->stw(CW_HIT_EXACT, 0u), store->stw(CW_REC, 0u);
+        ctr.nodes = ctr.prims = ctr.insts = ctr.exact = 0u;
         // NaN / empty-interval rays never hit anything (Embree: tnear <= t <= tfar)
-        done = !(ray.tmin <= ray.tmax);
+        done = !(tmin_ <= tmax_);
+    }
+    LCRT_HD void init(const BlobHeader *tlas, const Instance *instances_, const Ray *ray, uint32_t mask, Store *store_, Callbacks *cb_) {
+        init(reinterpret_cast<const u4 *>(reinterpret_cast<const char *>(tlas) + tlas->nodes_offset),
+             reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(tlas) + tlas->prims_offset), tlas->prim_count == 1u, instances_,
+             ray, mask, store_, cb_);
     }
 
-    LCRT_HD void accept(double t, float u, float v, uint32_t prim, uint32_t type) {
-        t_best = t;
-        // round the culling bound up so that the box test never rejects the accepted primitive's neighbours
-        float tf = (float)t;
-        if ((double)tf < t) tf = as_float(as_uint(tf) + (tf >= 0.f ? 1u : 0xffffffffu));
-        tmax = tf;
-        hit_inst = cur_inst, hit_prim = prim, hit_u = u, hit_v = v, hit_type = type;
+    // ---- result (valid once step() has returned false).  hit_rec / hit_pi locate a surface hit for refine_surface_hit.
+    LCRT_HD uint32_t hit_inst() const { return store->ldw(CW_HIT_INST); }
+    LCRT_HD uint32_t hit_prim() const { return store->ldw(CW_HIT_PRIM); }
+    LCRT_HD uint32_t hit_type() const { return store->ldw(CW_HIT_TYPE); }
+    LCRT_HD uint32_t hit_rec() const { return store->ldw(CW_HIT_REC); }
+    LCRT_HD uint32_t hit_pi() const { return store->ldw(CW_HIT_PI); }
+    LCRT_HD float hit_t() const { return as_float(store->ldw(CW_HIT_T)); }
+    LCRT_HD bool has_hit() const { return store->ldw(CW_HIT_INST) != ~0u; }
+
+    // final (inst, prim, t, u, v) with the double-precision refinement done in place (inline entry points, hostsim)
+    LCRT_HD void result(uint32_t &inst, uint32_t &prim, uint32_t &type, float &t, float &u, float &v) const {
+        inst = hit_inst(), prim = hit_prim(), type = MODE == MODE_QUERY ? hit_type() : (inst != ~0u ? (uint32_t)HIT_SURFACE : (uint32_t)HIT_MISS);
+        t = hit_t(), u = 0.f, v = 0.f;
+        if (type == HIT_SURFACE) refine_surface_hit(world, tlas_recs, hit_rec(), hit_pi(), prim, t, u, v);
+    }
+
+    LCRT_HD void accept(float t, float terr, uint32_t prim, uint32_t pi, uint32_t type, bool exact, double td) {
+        store->stw(CW_HIT_T, as_uint(t)), store->stw(CW_HIT_TERR, as_uint(terr));
+        store->stw(CW_HIT_INST, cur_inst), store->stw(CW_HIT_PRIM, prim);
+        store->stw(CW_HIT_REC, store->ldw(CW_REC)), store->stw(CW_HIT_PI, pi);
+        if (MODE == MODE_QUERY) store->stw(CW_HIT_TYPE, type);
+        store->stw(CW_HIT_EXACT, exact ? 1u : 0u);
+        if (exact) {
+            uint64_t bits;
+            memcpy(&bits, &td, 8);
+            store->stw(CW_HIT_TD_LO, (uint32_t)bits), store->stw(CW_HIT_TD_HI, (uint32_t)(bits >> 32));
+        }
+        // cull beyond the upper end of the accepted interval (a hair more: coincident primitives must still be
+        // visited so that the lowest (inst, prim) wins an exact tie)
+        tmax = fmaf(fabsf(t), 2.4e-7f, t + terr);
+    }
+
+    // (inst, prim) order for exact ties: the result must not depend on traversal order
+    LCRT_HD bool loses_tie(uint32_t prim) const {
+        const uint32_t hi = store->ldw(CW_HIT_INST);
+        return hi != ~0u && (cur_inst > hi || (cur_inst == hi && prim >= store->ldw(CW_HIT_PRIM)));
+    }
+
+    // exact t of the current best hit (evaluated on demand, then cached)
+    LCRT_HD double best_exact_t() {
+        if (store->ldw(CW_HIT_EXACT)) {
+            const uint64_t bits = ((uint64_t)store->ldw(CW_HIT_TD_HI) << 32) | store->ldw(CW_HIT_TD_LO);
+            double td;
+            memcpy(&td, &bits, 8);
+            return td;
+        }
+        double td = (double)hit_t();
+        if (MODE != MODE_QUERY || hit_type() == HIT_SURFACE) {
+            const InstanceRecord *r = tlas_recs + store->ldw(CW_HIT_REC);
+            const f4 *tr = reinterpret_cast<const f4 *>(reinterpret_cast<const char *>(r->prims) + (uint64_t)store->ldw(CW_HIT_PI) * sizeof(TriRecord));
+            float u, v;
+            double te;
+            if (COUNT) ctr.exact++;
+            if (tri_exact_world(world, r, tr, te, u, v)) td = te;
+        }
+        uint64_t bits;
+        memcpy(&bits, &td, 8);
+        store->stw(CW_HIT_TD_LO, (uint32_t)bits), store->stw(CW_HIT_TD_HI, (uint32_t)(bits >> 32)), store->stw(CW_HIT_EXACT, 1u);
+        return td;
     }
 
     LCRT_HD void leave_instance() {
         blas_sp = -1;
         nodes = tlas_nodes, prims = reinterpret_cast<const char *>(tlas_recs);
-        set_ray(world.ox, world.oy, world.oz, world.dx, world.dy, world.dz);
-        cur_inst = ~0u;
+        cur_inst = ~0u, cur_flags = 0u;
+        octinv = RAY_PENDING;
     }
 
-    LCRT_HD void enter_instance(const InstanceRecord *rec) {
+    LCRT_HD void enter_instance(uint32_t rec_index, const u4 r3, const u4 r4) {
         // keep what is left of the TLAS groups below the BLAS frames
-        if (G.y & 0xff000000u) stack->store(sp++, G);
-        if (Gt.y) stack->store(sp++, Gt);
+        if (G.y & 0xff000000u) store->store(sp++, G);
+        if (Gt.y & 0xffu) store->store(sp++, make_u2(Gt.x, Gt.y & 0xffu));
         Gt = make_u2(0u, 0u);
         blas_sp = sp;
-        const double *m = rec->inv;
-        const float i00 = (float)m[0], i01 = (float)m[1], i02 = (float)m[2], i03 = (float)m[3];
-        const float i10 = (float)m[4], i11 = (float)m[5], i12 = (float)m[6], i13 = (float)m[7];
-        const float i20 = (float)m[8], i21 = (float)m[9], i22 = (float)m[10], i23 = (float)m[11];
-        const float lox = fmaf(i00, world.ox, fmaf(i01, world.oy, fmaf(i02, world.oz, i03)));
-        const float loy = fmaf(i10, world.ox, fmaf(i11, world.oy, fmaf(i12, world.oz, i13)));
-        const float loz = fmaf(i20, world.ox, fmaf(i21, world.oy, fmaf(i22, world.oz, i23)));
-        const float ldx = fmaf(i00, world.dx, fmaf(i01, world.dy, i02 * world.dz));
-        const float ldy = fmaf(i10, world.dx, fmaf(i11, world.dy, i12 * world.dz));
-        const float ldz = fmaf(i20, world.dx, fmaf(i21, world.dy, i22 * world.dz));
-        set_ray(lox, loy, loz, ldx, ldy, ldz);
-        // |fl(o') - o'| <= ~4 eps * sum |inv_ij o_j| + |inv_i3|
-        const float ax = fabsf(world.ox), ay = fabsf(world.oy), az = fabsf(world.oz);
-        const float mx = fmaf(fabsf(i00), ax, fmaf(fabsf(i01), ay, fmaf(fabsf(i02), az, fabsf(i03))));
-        const float my = fmaf(fabsf(i10), ax, fmaf(fabsf(i11), ay, fmaf(fabsf(i12), az, fabsf(i13))));
-        const float mz = fmaf(fabsf(i20), ax, fmaf(fabsf(i21), ay, fmaf(fabsf(i22), az, fabsf(i23))));
-        oerr = 6.0e-7f * fmaxf(mx, fmaxf(my, mz));
-        cur_rec = rec;
-        nodes = reinterpret_cast<const u4 *>(rec->nodes);
-        prims = reinterpret_cast<const char *>(rec->prims);
-        cur_inst = rec->inst, cur_flags = rec->flags;
+        nodes = reinterpret_cast<const u4 *>(((uint64_t)r3.y << 32) | r3.x);
+        prims = reinterpret_cast<const char *>(((uint64_t)r3.w << 32) | r3.z);
+        cur_inst = r4.x, cur_flags = r4.z;
+        store->stw(CW_REC, rec_index);
         G = make_u2(0u, 0x80000000u);
+        octinv = RAY_PENDING;
         if (COUNT) ctr.insts++;
+    }
+
+    // (re)derive the current-space ray after a level change: the world ray, moved to object space by the fp32
+    // inverse when inside a non-identity instance.  One call site, so that lanes which start a ray, enter an
+    // instance or return from one share the same instructions.
+    LCRT_HD void setup_ray() {
+        const f4 w0 = ldg16(reinterpret_cast<const f4 *>(world)), w1 = ldg16(reinterpret_cast<const f4 *>(world) + 1);
+        float sox = w0.x, soy = w0.y, soz = w0.z, sdx = w1.x, sdy = w1.y, sdz = w1.z, oerr = 0.f, derr = 0.f;
+        if (blas_sp >= 0 && !(cur_flags & IREC_IDENTITY)) {
+            const f4 *rec = reinterpret_cast<const f4 *>(tlas_recs + store->ldw(CW_REC));
+            const f4 m0 = ldg16(rec), m1 = ldg16(rec + 1), m2 = ldg16(rec + 2);
+            sox = fmaf(m0.x, w0.x, fmaf(m0.y, w0.y, fmaf(m0.z, w0.z, m0.w)));
+            soy = fmaf(m1.x, w0.x, fmaf(m1.y, w0.y, fmaf(m1.z, w0.z, m1.w)));
+            soz = fmaf(m2.x, w0.x, fmaf(m2.y, w0.y, fmaf(m2.z, w0.z, m2.w)));
+            sdx = fmaf(m0.x, w1.x, fmaf(m0.y, w1.y, m0.z * w1.z));
+            sdy = fmaf(m1.x, w1.x, fmaf(m1.y, w1.y, m1.z * w1.z));
+            sdz = fmaf(m2.x, w1.x, fmaf(m2.y, w1.y, m2.z * w1.z));
+            // |fl(o') - o'_exact| <= 5 u * max_i (sum_j |inv_ij o_j| + |inv_i3|): entries rounded from double (1 u),
+            // three FFMA roundings; likewise for the direction
+            const float ax = fabsf(w0.x), ay = fabsf(w0.y), az = fabsf(w0.z);
+            const float mx = fmaf(fabsf(m0.x), ax, fmaf(fabsf(m0.y), ay, fmaf(fabsf(m0.z), az, fabsf(m0.w))));
+            const float my = fmaf(fabsf(m1.x), ax, fmaf(fabsf(m1.y), ay, fmaf(fabsf(m1.z), az, fabsf(m1.w))));
+            const float mz = fmaf(fabsf(m2.x), ax, fmaf(fabsf(m2.y), ay, fmaf(fabsf(m2.z), az, fabsf(m2.w))));
+            const float bx = fabsf(w1.x), by = fabsf(w1.y), bz = fabsf(w1.z);
+            const float nx = fmaf(fabsf(m0.x), bx, fmaf(fabsf(m0.y), by, fabsf(m0.z) * bz));
+            const float ny = fmaf(fabsf(m1.x), bx, fmaf(fabsf(m1.y), by, fabsf(m1.z) * bz));
+            const float nz = fmaf(fabsf(m2.x), bx, fmaf(fabsf(m2.y), by, fabsf(m2.z) * bz));
+            oerr = 5.0f * LCRT_U * fmaxf(mx, fmaxf(my, mz)), derr = 5.0f * LCRT_U * fmaxf(nx, fmaxf(ny, nz));
+        }
+        set_ray(sox, soy, soz, sdx, sdy, sdz, oerr, derr);
+    }
+
+    // one candidate triangle; returns true if the traversal terminates
+    LCRT_HD bool test_triangle(uint32_t pi) {
+        const f4 *tr = reinterpret_cast<const f4 *>(prims + (uint64_t)pi * sizeof(TriRecord));
+        const f4 v0 = ldg16(tr), v1 = ldg16(tr + 1), v2 = ldg16(tr + 2);
+        float t, terr;
+        const int verdict = tri_test_f32(ox, oy, oz, store->ld4(0), store->ld4(1), as_float(store->ldw(CW_SZ)), store->ldw(CW_KZ), v0, v1, v2, t, terr);
+        if (verdict == TRI_MISS) return false;
+        const uint32_t prim = as_uint(v0.w);
+        const bool candidate_program = MODE == MODE_QUERY && !(cur_flags & IREC_OPAQUE);
+        bool take = false, exact = false, need_exact = verdict == TRI_UNSURE || candidate_program;
+        double td = 0.0;
+        float u = 0.f, v = 0.f;
+        const float ht = hit_t(), he = as_float(store->ldw(CW_HIT_TERR));// he < 0: no hit yet, ht is the ray's tmax
+        if (!need_exact) {
+            // interval comparison: take / drop only what is certain (Embree: tnear <= t <= tfar, nearest wins)
+            const float hw = fmaxf(he, 0.f);
+            if (t - terr > ht + hw || t + terr < tmin) return false;
+            if (t - terr >= tmin && t + terr < ht - hw) take = true;
+            else need_exact = true;
+        }
+        if (need_exact) {
+            if (COUNT) ctr.exact++;
+            if (!tri_exact_world(world, tlas_recs + store->ldw(CW_REC), tr, td, u, v) || !(td >= (double)tmin)) return false;
+            if (he < 0.f) {
+                take = td <= (double)ht;
+            } else {
+                const double bd = best_exact_t();
+                take = td < bd || (td == bd && !loses_tie(prim));// exact ties go to the lower (inst, prim)
+            }
+            if (!take) return false;
+            t = (float)td, terr = 1.2e-7f * fabsf(t), exact = true;
+        }
+        if (candidate_program) {
+            Ray wr = *world;
+            wr.tmax = t;// accel.rs:663-672: tmax shrinks to the candidate while the callback runs
+            const CandidateResult r = cb->on_triangle(cur_inst, prim, u, v, t, wr);
+            if (r.committed) accept(t, terr, prim, pi, HIT_SURFACE, exact, td);
+            return r.terminated || (r.committed && MODE_ANY_QUERY());
+        }
+        accept(t, terr, prim, pi, HIT_SURFACE, exact, td);
+        return MODE == MODE_ANY || MODE_ANY_QUERY();
     }
 
     // returns true while there is more work
     LCRT_HD bool step() {
         if (done) return false;
-        if (G.y & 0xff000000u) {
-            // ---- one internal node
-            const int child_bit = bfind(G.y);
-            const uint32_t base = G.x;
-            G.y &= ~(1u << child_bit);
-            const uint32_t imask_parent = G.y & 0xffu;
-            if (G.y & 0xff000000u) stack->store(sp++, G);
-            const uint32_t slot = (uint32_t)(child_bit - 24) ^ (octinv4 & 0xffu);
-            const uint32_t rel = (uint32_t)popc(imask_parent & ~(0xffffffffu << slot));
-            const u4 *n = nodes + (uint64_t)(base + rel) * 5u;
-            const u4 n0 = n[0], n1 = n[1], n2 = n[2], n3 = n[3], n4 = n[4];
-            if (COUNT) ctr.nodes++;
-            const uint32_t hits = intersect_node8(n0, n1, n2, n3, n4, ox, oy, oz, idx, idy, idz, tmin, tmax, octinv4);
-            G = make_u2(n1.x, (hits & 0xff000000u) | (n0.w >> 24));
-            Gt = make_u2(n1.y, hits & 0x00ffffffu);
-        } else {
-            Gt = G;
-            G = make_u2(0u, 0u);
-        }
-        // ---- primitives exposed by that node
-        while (Gt.y) {
-            const int bit = bfind(Gt.y);
-            Gt.y &= ~(1u << bit);
-            const uint32_t pi = Gt.x + (uint32_t)bit;
-            if (blas_sp < 0) {
-                // TLAS leaf: an instance
-                const InstanceRecord *rec = tlas_recs + pi;
-                const u4 r4 = reinterpret_cast<const u4 *>(rec)[7];// { inst, mask, flags, pad }
-                const uint32_t kind = r4.z & IREC_KIND_MASK;
-                if ((r4.y & ray_mask) == 0u) continue;
-                if (MODE != MODE_QUERY && kind != KIND_TRIANGLES) continue;// intersect() does not see procedural prims
-                enter_instance(rec);
-                break;
-            }
-            if (COUNT) ctr.prims++;
-            if ((cur_flags & IREC_KIND_MASK) == KIND_TRIANGLES) {
-                const f4 *tr = reinterpret_cast<const f4 *>(prims + (uint64_t)pi * sizeof(TriRecord));
-                const f4 v0 = tr[0], v1 = tr[1], v2 = tr[2];
-                if (!tri_prefilter(ox, oy, oz, dx, dy, dz, oerr, v0, v1, v2)) continue;
-                double t, u, v;
-                {
-                    // exact test on the object-space ray re-derived in double from the world ray
-                    const double *m = cur_rec->inv;
-                    const double wox = world.ox, woy = world.oy, woz = world.oz, wdx = world.dx, wdy = world.dy, wdz = world.dz;
-                    const double eox = m[0] * wox + m[1] * woy + m[2] * woz + m[3], eoy = m[4] * wox + m[5] * woy + m[6] * woz + m[7],
-                                 eoz = m[8] * wox + m[9] * woy + m[10] * woz + m[11];
-                    const double edx = m[0] * wdx + m[1] * wdy + m[2] * wdz, edy = m[4] * wdx + m[5] * wdy + m[6] * wdz,
-                                 edz = m[8] * wdx + m[9] * wdy + m[10] * wdz;
-                    if (!tri_exact(eox, eoy, eoz, edx, edy, edz, v0, v1, v2, t, u, v)) continue;
-                }
-                if (t < (double)tmin || t > t_best) continue;// Embree: tnear <= t <= tfar
-                const uint32_t prim = as_uint(v0.w);
-                // exact ties are resolved towards the lower (inst, prim) so the result does not depend on traversal order
-                if (t == t_best && hit_inst != ~0u && (cur_inst > hit_inst || (cur_inst == hit_inst && prim >= hit_prim))) continue;
-                if (MODE == MODE_QUERY && !(cur_flags & IREC_OPAQUE)) {
-                    Ray wr = world;
-                    wr.tmax = (float)t;// accel.rs:663-672: tmax shrinks to the candidate while the callback runs
-                    const CandidateResult r = cb->on_triangle(cur_inst, prim, (float)u, (float)v, (float)t, wr);
-                    if (r.committed) accept(t, (float)u, (float)v, prim, HIT_SURFACE);
-                    if (r.terminated || (r.committed && MODE_ANY_QUERY())) {
-                        done = true;
-                        return false;
-                    }
-                    continue;
-                }
-                accept(t, (float)u, (float)v, prim, HIT_SURFACE);
-                if (MODE == MODE_ANY || MODE_ANY_QUERY()) {
-                    done = true;
-                    return false;
-                }
-            } else if (MODE == MODE_QUERY) {
-                // procedural primitive: conservative box test, then the candidate program decides
-                const f4 *br = reinterpret_cast<const f4 *>(prims + (uint64_t)pi * sizeof(BoxRecord));
-                const f4 lo = br[0], hi = br[1];
-                if (!slab_conservative(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, ox, oy, oz, idx, idy, idz, tmin, tmax)) continue;
-                Ray wr = world;
-                wr.tmax = tmax;
-                const uint32_t prim = as_uint(lo.w);
-                const CandidateResult r = cb->on_procedural(cur_inst, prim, wr, instances, lo, hi);
-                if (r.committed && r.t_hit >= tmin && (double)r.t_hit < t_best) {// accel.rs:711-713
-                    accept((double)r.t_hit, 0.f, 0.f, prim, HIT_PROCEDURAL);
-                    if (MODE_ANY_QUERY()) {
-                        done = true;
-                        return false;
-                    }
-                }
-                if (r.terminated) {
-                    done = true;
-                    return false;
-                }
-            }
-        }
-        // ---- pop
+        // ---- pop when both groups are exhausted
         if ((G.y & 0xff000000u) == 0u && Gt.y == 0u) {
             if (blas_sp >= 0 && sp == blas_sp) leave_instance();
             if (sp == 0) {
                 done = true;
                 return false;
             }
-            G = stack->load(--sp);
+            const u2 e = store->load(--sp);
+            if (e.y & 0xff000000u) G = e;
+            else Gt = e;
+        }
+        if (octinv == RAY_PENDING && (blas_sp >= 0 || (G.y & 0xff000000u) != 0u)) setup_ray();
+        // ---- one internal node (not while primitives of the previous node are pending: they may shrink tmax)
+        if ((G.y & 0xff000000u) != 0u && Gt.y == 0u) {
+            const int child_bit = bfind(G.y);
+            const uint32_t base = G.x;
+            G.y &= ~(1u << child_bit);
+            const uint32_t imask_parent = G.y & 0xffu;
+            if (G.y & 0xff000000u) store->store(sp++, G);
+            const uint32_t slot = (uint32_t)(child_bit - 24) ^ octinv;
+            const uint32_t rel = (uint32_t)popc(imask_parent & ~(0xffffffffu << slot));
+            const uint32_t ni = base + rel;
+            const u4 *n = nodes + (uint64_t)ni * 5u;
+            const u4 n0 = ldg16(n), n2 = ldg16(n + 2), n3 = ldg16(n + 3), n4 = ldg16(n + 4);
+            const uint32_t child_base = ldg16(n + 1).x;
+            if (COUNT) ctr.nodes++;
+            const uint32_t hm = intersect_node8(n0, n2, n3, n4, ox, oy, oz, idx, idy, idz, tmin, tmax, magic);
+            const uint32_t imask = n0.w >> 24;
+            G = make_u2(child_base, (permute_slots(hm & imask, octinv) << 24) | imask);
+            Gt = make_u2(ni, hm & ~imask);
+        }
+        // ---- one primitive
+        if (Gt.y != 0u) {
+            if ((Gt.y >> 8) == 0u) {
+                // open the nearest hit leaf slot (octant order): its records are prim_base + offset .. + count
+                const uint32_t k = octinv & 7u;
+                const uint32_t s = (uint32_t)bfind(permute_slots(Gt.y, k)) ^ k;
+                Gt.y &= ~(1u << s);
+                const u4 n1 = ldg16(nodes + (uint64_t)Gt.x * 5u + 1);
+                const uint32_t meta = (((s & 4u) ? n1.w : n1.z) >> (8u * (s & 3u))) & 0xffu;
+                const uint32_t unary = meta >> 5;// 0 (empty slot), 1, 3 or 7
+                tp = n1.y + (meta & 31u);
+                Gt.y |= ((unary & 1u) + ((unary >> 1) & 1u) + (unary >> 2)) << 8;
+            }
+            if ((Gt.y >> 8) != 0u) {
+                Gt.y -= 1u << 8;
+                const uint32_t pi = tp++;
+                if (blas_sp < 0) {
+                    // TLAS leaf: an instance
+                    const u4 *rec = reinterpret_cast<const u4 *>(tlas_recs + pi);
+                    const u4 r4 = ldg16(rec + 4);// { inst, mask, flags, pad }
+                    if ((r4.y & ray_mask) != 0u && (MODE == MODE_QUERY || (r4.z & IREC_KIND_MASK) == KIND_TRIANGLES))
+                        enter_instance(pi, ldg16(rec + 3), r4);// intersect() does not see procedural prims
+                } else if ((cur_flags & IREC_KIND_MASK) == KIND_TRIANGLES) {
+                    if (COUNT) ctr.prims++;
+                    if (test_triangle(pi)) {
+                        done = true;
+                        return false;
+                    }
+                } else if (MODE == MODE_QUERY) {
+                    if (COUNT) ctr.prims++;
+                    // procedural primitive: conservative box test, then the candidate program decides
+                    const f4 *br = reinterpret_cast<const f4 *>(prims + (uint64_t)pi * sizeof(BoxRecord));
+                    const f4 lo = ldg16(br), hi = ldg16(br + 1);
+                    if (slab_conservative(lo.x, lo.y, lo.z, hi.x, hi.y, hi.z, ox, oy, oz, idx, idy, idz, tmin, tmax)) {
+                        Ray wr = *world;
+                        // the program sees the committed distance so far; a surface hit reports its exact value
+                        const float ht = store->ldw(CW_HIT_INST) != ~0u ? (float)best_exact_t() : hit_t();
+                        wr.tmax = ht;
+                        const uint32_t prim = as_uint(lo.w);
+                        const CandidateResult r = cb->on_procedural(cur_inst, prim, wr, instances, lo, hi);
+                        if (r.committed && r.t_hit >= tmin && r.t_hit < ht) {// accel.rs:711-713
+                            accept(r.t_hit, 0.f, prim, pi, HIT_PROCEDURAL, true, (double)r.t_hit);
+                            if (MODE_ANY_QUERY()) {
+                                done = true;
+                                return false;
+                            }
+                        }
+                        if (r.terminated) {
+                            done = true;
+                            return false;
+                        }
+                    }
+                }
+            }
         }
         return true;
     }
-
-    bool terminate_on_first = false;// query_any
-    LCRT_HD bool MODE_ANY_QUERY() const { return MODE == MODE_QUERY && terminate_on_first; }
 };
 
 }// namespace lcrt

@@ -239,30 +239,33 @@ void hs_trace_closest(const void *tlas, const void *instances, const void *rays_
                       void *hits_, uint64_t *counters) {
     const Ray *rays = static_cast<const Ray *>(rays_);
     SurfaceHit *hits = static_cast<SurfaceHit *>(hits_);
-    uint64_t cn = 0, cp = 0, ci = 0;
+    uint64_t cn = 0, cp = 0, ci = 0, ce = 0;
     for (uint64_t i = 0; i < n; i++) {
-        LocalStack st;
+        LocalStore st;
         NoCallbacks cb;
-        Traversal<MODE_CLOSEST, true, LocalStack, NoCallbacks> tr;
-        tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
+        Traversal<MODE_CLOSEST, true, LocalStore, NoCallbacks> tr;
+        tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
         while (tr.step()) {}
         SurfaceHit h;
-        h.inst = tr.hit_inst, h.prim = tr.hit_prim, h.u = tr.hit_u, h.v = tr.hit_v, h.t = tr.hit_inst == ~0u ? rays[i].tmax : (float)tr.t_best, h.pad = 0;
+        uint32_t type;
+        tr.result(h.inst, h.prim, type, h.t, h.u, h.v);
+        h.pad = 0;
+        if (type == HIT_MISS) h.t = rays[i].tmax;
         hits[i] = h;
-        cn += tr.ctr.nodes, cp += tr.ctr.prims, ci += tr.ctr.insts;
+        cn += tr.ctr.nodes, cp += tr.ctr.prims, ci += tr.ctr.insts, ce += tr.ctr.exact;
     }
-    if (counters) counters[0] = cn, counters[1] = cp, counters[2] = ci;
+    if (counters) counters[0] = cn, counters[1] = cp, counters[2] = ci, counters[3] = ce;
 }
 
 void hs_trace_any(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, uint32_t *out) {
     const Ray *rays = static_cast<const Ray *>(rays_);
     for (uint64_t i = 0; i < n; i++) {
-        LocalStack st;
+        LocalStore st;
         NoCallbacks cb;
-        Traversal<MODE_ANY, false, LocalStack, NoCallbacks> tr;
-        tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
+        Traversal<MODE_ANY, false, LocalStore, NoCallbacks> tr;
+        tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
         while (tr.step()) {}
-        out[i] = tr.hit_inst != ~0u ? 1u : 0u;
+        out[i] = tr.has_hit() ? 1u : 0u;
     }
 }
 
@@ -271,15 +274,15 @@ void hs_query(const void *tlas, const void *instances, const void *rays_, uint64
     const Ray *rays = static_cast<const Ray *>(rays_);
     CommittedHit *hits = static_cast<CommittedHit *>(hits_);
     for (uint64_t i = 0; i < n; i++) {
-        LocalStack st;
+        LocalStore st;
         BuiltinPrograms cb{tri_prog, proc_prog};
-        Traversal<MODE_QUERY, false, LocalStack, BuiltinPrograms> tr;
-        tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
+        Traversal<MODE_QUERY, false, LocalStore, BuiltinPrograms> tr;
+        tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
         tr.terminate_on_first = terminate_on_first != 0;
         while (tr.step()) {}
         CommittedHit h;
-        h.inst = tr.hit_inst, h.prim = tr.hit_prim, h.u = tr.hit_u, h.v = tr.hit_v, h.hit_type = tr.hit_type;
-        h.t = tr.hit_type == HIT_MISS ? rays[i].tmax : (float)tr.t_best;
+        tr.result(h.inst, h.prim, h.hit_type, h.t, h.u, h.v);
+        if (h.hit_type == HIT_MISS) h.t = rays[i].tmax;
         hits[i] = h;
     }
 }

@@ -139,7 +139,7 @@ class SimAccel:
         rays = np.ascontiguousarray(rays)
         m, ms = self._masks(mask, len(rays))
         hits = np.zeros(len(rays), dtype=S.HIT_DTYPE)
-        ctr = np.zeros(3, dtype=np.uint64)
+        ctr = np.zeros(4, dtype=np.uint64)
         lib().hs_trace_closest(_p(self.blob), _p(self.instances), _p(rays), len(rays), _p(m), ms, _p(hits), _p(ctr))
         return (hits, ctr) if want_counters else hits
 
