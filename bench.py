@@ -285,8 +285,8 @@ def main():
     acc.trace_closest(d_bounce, out=d_hits_b, counters=ctr_b)
     torch.cuda.synchronize()
     cp, cb = ctr_p.cpu().numpy() / n, ctr_b.cpu().numpy() / n
-    bytes_p = 32 + 24 + cp[0] * 80 + cp[1] * 48 + cp[2] * 128
-    bytes_b = 32 + 24 + cb[0] * 80 + cb[1] * 48 + cb[2] * 128
+    bytes_p = 32 + 24 + cp[0] * 80 + cp[1] * 48 + cp[2] * 80
+    bytes_b = 32 + 24 + cb[0] * 80 + cb[1] * 48 + cb[2] * 80
 
     # ------------------------------------------------------------------ timed region
     K, W = args.steps, max(args.warmup, 3)

@@ -26,7 +26,8 @@ import numpy as np
 from . import scenes  # noqa: F401  (host-side scene generators)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblcb200_rt.so")
+# LCB200_RT_LIB: developer override used by tools/trace_perf.py to time differently tuned builds of the same library
+LIB_PATH = os.environ.get("LCB200_RT_LIB") or os.path.join(_HERE, "liblcb200_rt.so")
 _LIB = None
 
 KIND_TRIANGLES, KIND_AABBS, KIND_INSTANCES = 0, 1, 2

@@ -209,7 +209,7 @@ struct Bvh2 {
     f4 *lo, *hi;           // [2n-1]
     u2 *child;             // [n-1]
     u2 *range;             // [n-1]  (left end set by the left child, right end by the right child)
-    uint32_t *flag;        // [n-1]  zero-initialised arrival counters
+    uint32_t *flag;        // [n-1]  zero-initialised arrival counters; once a node is complete: its number of leaf slots
     uint32_t *root;        // [1]
     float ci;              // cost of one binary split relative to one primitive test
     uint32_t max_leaf;
@@ -234,10 +234,11 @@ LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
     f4 lo = make_f4(leaf_box.lo[0], leaf_box.lo[1], leaf_box.lo[2], 0.f);
     f4 hi = make_f4(leaf_box.hi[0], leaf_box.hi[1], leaf_box.hi[2], 0.f);
     float cost = area_of(lo, hi);
-    uint32_t count = 1u, mark = LEAF_MARK;
+    uint32_t count = 1u, mark = LEAF_MARK, slots = 1u;
     for (;;) {
         lo.w = cost, hi.w = as_float(count | mark);
         t.lo[cur] = lo, t.hi[cur] = hi;
+        if (cur < n - 1u) t.flag[cur] = slots;// the arrival counter has done its job
         if (left == 0u && right == n - 1u) {
             *t.root = cur;
             return;
@@ -262,10 +263,11 @@ LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
         lo.x = fminf(lo.x, slo.x), lo.y = fminf(lo.y, slo.y), lo.z = fminf(lo.z, slo.z);
         hi.x = fmaxf(hi.x, shi.x), hi.y = fmaxf(hi.y, shi.y), hi.z = fmaxf(hi.z, shi.z);
         count += as_uint(shi.w) & ~LEAF_MARK;
+        slots += sib < n - 1u ? LCRT_VOLATILE_LOAD_U32(&t.flag[sib]) : 1u;
         const float area = area_of(lo, hi);
         const float c_split = t.ci * area + cost + slo.w;
         const float c_leaf = area * (float)count;
-        if (count <= t.max_leaf && c_leaf <= c_split) cost = c_leaf, mark = LEAF_MARK;
+        if (count <= t.max_leaf && c_leaf <= c_split) cost = c_leaf, mark = LEAF_MARK, slots = 1u;
         else cost = c_split, mark = 0u;
         cur = parent;
     }
@@ -374,16 +376,45 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
             nc = 2;
         }
     }
-    // greedy surface-area opening until eight children
+    // Opening policy.  Every wide node below the top levels should be as full as possible, so the binary subtree is
+    // opened by leaf-slot counts (lbvh_climb leaves them in flag[]):
+    //   * a subtree of <= 8 leaf slots becomes ONE wide node whose children are all leaves;
+    //   * otherwise children with more than 8 leaf slots are opened first, largest surface area first (the classic
+    //     greedy rule, which is what the upper levels see);
+    //   * then, smallest first, children small enough to be dissolved into leaf slots of this node entirely are
+    //     dissolved; what is left (<= 8 leaf slots each) becomes full-ish all-leaf nodes one level down.
+    auto slots_of = [&](uint32_t id) -> uint32_t { return id < t.n - 1u ? t.flag[id] : 1u; };
+    uint32_t cslots[8];
+    for (int k = 0; k < nc; k++) cslots[k] = cleaf[k] ? 1u : slots_of(cid[k]);
+    auto open_child = [&](int k) {
+        const u2 ch = t.child[cid[k]];
+        load_child(k, ch.x), cslots[k] = cleaf[k] ? 1u : slots_of(ch.x);
+        load_child(nc, ch.y), cslots[nc] = cleaf[nc] ? 1u : slots_of(ch.y);
+        nc++;
+    };
     while (nc < 8) {
         int best = -1;
         float ba = -1.f;
         for (int k = 0; k < nc; k++)
-            if (!cleaf[k] && carea[k] > ba) ba = carea[k], best = k;
+            if (!cleaf[k] && cslots[k] > 8u && carea[k] > ba) ba = carea[k], best = k;
         if (best < 0) break;
-        const u2 ch = t.child[cid[best]];
-        load_child(best, ch.x);
-        load_child(nc++, ch.y);
+        open_child(best);
+    }
+    for (;;) {
+        int best = -1;
+        uint32_t bs = 0xffffffffu;
+        for (int k = 0; k < nc; k++)
+            if (!cleaf[k] && (uint32_t)nc - 1u + cslots[k] <= 8u && cslots[k] < bs) bs = cslots[k], best = k;
+        if (best < 0) break;
+        // dissolve the whole subtree of that child: every opening yields pieces that still fit
+        uint32_t pending = 1u << best;
+        while (pending) {
+            const int k = bfind(pending);
+            pending &= ~(1u << k);
+            if (cleaf[k]) continue;
+            open_child(k);
+            pending |= (1u << k) | (1u << (nc - 1));
+        }
     }
     Box nb = box_empty();
     for (int k = 0; k < nc; k++) box_grow(nb, cbox[k]);

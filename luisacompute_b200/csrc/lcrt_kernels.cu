@@ -213,8 +213,11 @@ __global__ void k_update_handles(Instance *instances, const InstanceHandleUpdate
 constexpr int TRACE_BLOCK = 128;
 constexpr int TRACE_SMEM_STACK = 8;   // stack entries per thread kept in shared memory
 constexpr uint32_t TRACE_BATCH = 128; // rays a warp reserves per atomic
+#ifndef LCRT_TRACE_MIN_BLOCKS
+#define LCRT_TRACE_MIN_BLOCKS 5     // resident blocks per SM the register allocation is bounded for
+#endif
 #ifndef LCRT_REFILL_MIN
-#define LCRT_REFILL_MIN 6             // idle lanes that trigger a warp-cooperative refill
+#define LCRT_REFILL_MIN 12            // idle lanes that trigger a warp-cooperative refill
 #endif
 
 // Per-thread storage outside the register file (see LocalStore in lcrt_traverse.h): every array is laid out
@@ -265,7 +268,7 @@ struct TraceParams {
 // ray by one step() per iteration.  Surface hits are written in a provisional form (u = TLAS record index, prim =
 // primitive record index, t = fp32 distance) that k_refine_hits turns into the final record.
 template<int MODE, bool COUNT, class Callbacks>
-__global__ void __launch_bounds__(TRACE_BLOCK, 5) k_trace(TraceParams p) {
+__global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(TraceParams p) {
     HybridStore store;
     Callbacks cb;
     if constexpr (MODE == MODE_QUERY) cb = Callbacks{p.tri_prog, p.proc_prog};
@@ -277,14 +280,33 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 5) k_trace(TraceParams p) {
     const bool single = p.tlas->prim_count == 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
-    bool active = false;
+    bool active = false, unsaved = false;// unsaved: this lane's finished ray has not been written yet
     uint64_t warp_next = 0, warp_end = 0;// this warp's reserved range of ray indices
     unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0, c_exact = 0;
     bool exhausted = false;
     for (;;) {
-        // ---- warp-cooperative refill of idle lanes
+        // ---- warp-cooperative retire + refill of idle lanes
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && !exhausted && ((uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN || idle == 0xffffffffu)) {
+        if (idle && ((!exhausted && (uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN) || idle == 0xffffffffu)) {
+            if (unsaved) {
+                // results are written here, together by all lanes that finished since the last refill
+                const uint64_t ray_idx = (uint64_t)(tr.world - p.rays);
+                const bool hit = tr.has_hit();
+                if constexpr (MODE == MODE_CLOSEST) {
+                    u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
+                    o[0] = make_u2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u), o[1] = make_u2(hit ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(as_uint(tr.hit_t()), 0u);
+                } else if constexpr (MODE == MODE_ANY) {
+                    static_cast<uint32_t *>(p.out)[ray_idx] = hit ? 1u : 0u;
+                } else {
+                    const uint32_t type = tr.hit_type();
+                    u2 *o = reinterpret_cast<u2 *>(static_cast<CommittedHit *>(p.out) + ray_idx);
+                    o[0] = make_u2(tr.hit_inst(), type == HIT_SURFACE ? tr.hit_pi() : tr.hit_prim());
+                    o[1] = make_u2(type == HIT_SURFACE ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(type, as_uint(tr.hit_t()));
+                }
+                if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts, c_exact += tr.ctr.exact;
+                unsaved = false;
+            }
+            if (exhausted) break;// every lane idle and nothing left to fetch
             const uint32_t want = (uint32_t)__popc(idle);
             if (warp_next == warp_end) {
                 unsigned long long base = 0;
@@ -303,27 +325,9 @@ __global__ void __launch_bounds__(TRACE_BLOCK, 5) k_trace(TraceParams p) {
                 active = true;
             }
             warp_next += want < avail ? want : avail;
-        } else if (idle == 0xffffffffu) {
-            break;
         }
         // ---- one traversal step per lane
-        if (active && !tr.step()) {
-            const uint64_t ray_idx = (uint64_t)(tr.world - p.rays);
-            const bool hit = tr.has_hit();
-            if constexpr (MODE == MODE_CLOSEST) {
-                u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
-                o[0] = make_u2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u), o[1] = make_u2(hit ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(as_uint(tr.hit_t()), 0u);
-            } else if constexpr (MODE == MODE_ANY) {
-                static_cast<uint32_t *>(p.out)[ray_idx] = hit ? 1u : 0u;
-            } else {
-                const uint32_t type = tr.hit_type();
-                u2 *o = reinterpret_cast<u2 *>(static_cast<CommittedHit *>(p.out) + ray_idx);
-                o[0] = make_u2(tr.hit_inst(), type == HIT_SURFACE ? tr.hit_pi() : tr.hit_prim());
-                o[1] = make_u2(type == HIT_SURFACE ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(type, as_uint(tr.hit_t()));
-            }
-            if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts, c_exact += tr.ctr.exact;
-            active = false;
-        }
+        if (active && !tr.step()) active = false, unsaved = true;
     }
     if constexpr (COUNT) {
 #pragma unroll

@@ -92,6 +92,17 @@ LCRT_HD float safe_dir(float d) {
     return fabsf(d) < 1e-20f ? copysignf(1e-20f, d) : d;
 }
 
+// reciprocal within 1 ulp (MUFU.RCP on the device); used only where the error analysis budgets 2 u for it
+LCRT_HD float rcp_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
 // 16-byte read-only loads of BVH data (never written while a trace is in flight)
 template<class T>
 LCRT_HD T ldg16(const T *p) {
@@ -193,10 +204,10 @@ enum TriVerdict : int { TRI_MISS = 0, TRI_HIT = 1, TRI_UNSURE = 2 };
 // with kz the dominant axis of d), so (A.r1, A.r2) are the coordinates of A in the plane z' = 0 of a frame whose z'
 // axis is the ray; the 2D edge functions equal the exact scalar triple products d.(B x C) / d_kz.
 //   r1.w = 2 * (absolute error bound of the fp32 ray origin, 0 for untransformed rays)
-//   r2.w = 3 u + (error bound of the shear entries beyond their own rounding, 0 for untransformed rays)
+//   r2.w = 4 u + (error bound of the shear entries beyond their own 2 u, 0 for untransformed rays)
 // Error model (DESIGN.md "triangle test"): with bm the largest |component| of the ray-relative vertices and m2 the
 // largest |2D coordinate|, every 2D coordinate is within e = bm * r2.w + r1.w + u * m2 of its exact value
-// (subtraction, shear product, shear entry, FFMA rounding), an edge function within 4 e m2 + 2 e^2 + 4 u m2^2.
+// (subtraction u, shear product u, shear entry 2 u, FFMA rounding), an edge function within 4 e m2 + 2 e^2 + 4 u m2^2.
 // The bound E carries 25 % head room.  TRI_HIT: all three edge functions exceed E with the same sign; TRI_MISS: two
 // of them provably differ in sign; everything else (including NaN) is TRI_UNSURE.  For TRI_HIT, t is the fp32
 // distance and terr a bound of |t - t_exact|.
@@ -225,13 +236,13 @@ LCRT_HD int tri_test_f32(float ox, float oy, float oz, const f4 r1, const f4 r2,
     const float za = (kz == 0u ? Ax : kz == 1u ? Ay : Az) * sz, zb = (kz == 0u ? Bx : kz == 1u ? By : Bz) * sz,
                 zc = (kz == 0u ? Cx : kz == 1u ? Cy : Cz) * sz;
     const float T = fmaf(U, za, fmaf(V, zb, W * zc));
-    const float rdet = 1.0f / det;
+    const float rdet = rcp_fast(det);// 2 u, budgeted below
     t = T * rdet;
     // |b_i - b_i_exact| <= 4 E / |det| and the errors sum to zero, so they move t by at most 6 (E / |det|) zspread;
-    // the z_i are within (r2.w + 3 u) zmax + |sz| oerr of exact; the accumulation and the division add 6 u zmax.
+    // the z_i are within (r2.w + 3 u) zmax + |sz| oerr of exact; the accumulation and the division add 8 u zmax.
     const float zmax = fmaxf(fabsf(za), fmaxf(fabsf(zb), fabsf(zc)));
     const float zspread = fmaxf(za, fmaxf(zb, zc)) - fminf(za, fminf(zb, zc));
-    terr = 1.25f * fmaf(6.0f * E * fabsf(rdet), zspread, fmaf(cerr + 9.0f * LCRT_U, zmax, fabsf(sz) * oerr2));
+    terr = 1.25f * fmaf(6.0f * E * fabsf(rdet), zspread, fmaf(cerr + 11.0f * LCRT_U, zmax, fabsf(sz) * oerr2));
     return terr == terr ? TRI_HIT : TRI_UNSURE;
 }
 
@@ -359,24 +370,25 @@ struct Traversal {
     LCRT_HD void set_ray(float ox_, float oy_, float oz_, float dx, float dy, float dz, float oerr, float derr) {
         ox = ox_, oy = oy_, oz = oz_;
         const float sdx = safe_dir(dx), sdy = safe_dir(dy), sdz = safe_dir(dz);
-        idx = 1.0f / sdx, idy = 1.0f / sdy, idz = 1.0f / sdz;
+        // 1 ulp reciprocals: the box test budgets 10 u per coefficient and uses at most 7 with these (axis_coef)
+        idx = rcp_fast(sdx), idy = rcp_fast(sdy), idz = rcp_fast(sdz);
         const uint32_t oct = (sdx < 0.f ? 1u : 0u) | (sdy < 0.f ? 2u : 0u) | (sdz < 0.f ? 4u : 0u);
         octinv = 7u - oct;
-        // shear rows for the triangle test: kz = dominant axis, (kx, ky, kz) cyclic
+        // shear rows for the triangle test: kz = dominant axis, (kx, ky, kz) cyclic.  Branch-free on purpose.
         const float adx = fabsf(dx), ady = fabsf(dy), adz = fabsf(dz);
-        const uint32_t kz = (adx >= ady && adx >= adz) ? 0u : (ady >= adz ? 1u : 2u);
-        const float dk = kz == 0u ? dx : kz == 1u ? dy : dz;
-        const float dkx = kz == 0u ? dy : kz == 1u ? dz : dx;
-        const float dky = kz == 0u ? dz : kz == 1u ? dx : dy;
-        const float nsx = -(dkx / dk), nsy = -(dky / dk);// NaN for a null direction: every test becomes TRI_UNSURE
+        const bool k0 = adx >= ady && adx >= adz, k1 = !k0 && ady >= adz, k2 = !k0 && !k1;
+        const float dk = k0 ? dx : k1 ? dy : dz;
+        const float dkx = k0 ? dy : k1 ? dz : dx;
+        const float dky = k0 ? dz : k1 ? dx : dy;
+        const float rk = 1.0f / dk;// correctly rounded; NaN / inf for a null direction: every test becomes TRI_UNSURE
+        const float nsx = -(dkx * rk), nsy = -(dky * rk);// within 2 u of exact
         f4 r1, r2;
-        if (kz == 0u) r1 = make_f4(nsx, 1.f, 0.f, 0.f), r2 = make_f4(nsy, 0.f, 1.f, 0.f);
-        else if (kz == 1u) r1 = make_f4(0.f, nsx, 1.f, 0.f), r2 = make_f4(1.f, nsy, 0.f, 0.f);
-        else r1 = make_f4(1.f, 0.f, nsx, 0.f), r2 = make_f4(0.f, 1.f, nsy, 0.f);
+        r1.x = k2 ? 1.f : k0 ? nsx : 0.f, r1.y = k0 ? 1.f : k1 ? nsx : 0.f, r1.z = k1 ? 1.f : k2 ? nsx : 0.f;
+        r2.x = k1 ? 1.f : k0 ? nsy : 0.f, r2.y = k2 ? 1.f : k1 ? nsy : 0.f, r2.z = k0 ? 1.f : k2 ? nsy : 0.f;
         r1.w = 2.0f * oerr;
-        r2.w = 3.0f * LCRT_U + 2.5f * derr / fabsf(dk);
+        r2.w = 4.0f * LCRT_U + 2.5f * derr * fabsf(rk);
         store->st4(0, r1), store->st4(1, r2);
-        store->stw(CW_SZ, as_uint(1.0f / dk)), store->stw(CW_KZ, kz);
+        store->stw(CW_SZ, as_uint(rk)), store->stw(CW_KZ, k0 ? 0u : k1 ? 1u : 2u);
     }
 
     // `single`: the TLAS holds exactly one instance (record 0): its root node is skipped
@@ -605,9 +617,8 @@ struct Traversal {
         // ---- one primitive
         if (Gt.y != 0u) {
             if ((Gt.y >> 8) == 0u) {
-                // open the nearest hit leaf slot (octant order): its records are prim_base + offset .. + count
-                const uint32_t k = octinv & 7u;
-                const uint32_t s = (uint32_t)bfind(permute_slots(Gt.y, k)) ^ k;
+                // open the next hit leaf slot: its records are prim_base + offset .. + count
+                const uint32_t s = (uint32_t)bfind(Gt.y);
                 Gt.y &= ~(1u << s);
                 const u4 n1 = ldg16(nodes + (uint64_t)Gt.x * 5u + 1);
                 const uint32_t meta = (((s & 4u) ? n1.w : n1.z) >> (8u * (s & 3u))) & 0xffu;
