@@ -234,6 +234,7 @@ __device__ __forceinline__ TraceSmem *trace_smem() {
     return reinterpret_cast<TraceSmem *>(lcrt_trace_smem);
 }
 struct HybridStore {
+    static constexpr bool world_in_global = true;
     u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
     __device__ __forceinline__ void store(int i, u2 v) {
         if (i < TRACE_SMEM_STACK) trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] = v;

@@ -76,6 +76,7 @@ enum ColdWord : int {
     CW_COUNT
 };
 struct LocalStore {
+    static constexpr bool world_in_global = false;
     u2 e[LCRT_STACK_SIZE];
     f4 rows[2];
     uint32_t words[CW_COUNT];
@@ -366,6 +367,14 @@ struct Traversal {
     static constexpr uint32_t RAY_PENDING = 0xffffffffu;// octinv value: the current-space ray must be (re)derived
     LCRT_HD bool MODE_ANY_QUERY() const { return MODE == MODE_QUERY && terminate_on_first; }
 
+    // the world ray lives in global memory for the batch kernels (read-only path) and in the caller's local memory for
+    // the inline entry points
+    LCRT_HD f4 load_world(int k) const {
+        const f4 *p = reinterpret_cast<const f4 *>(world) + k;
+        if (Store::world_in_global) return ldg16(p);
+        return *p;
+    }
+
     // oerr: bound of |o - o_exact| per component; derr: likewise for d (both 0 for the untransformed ray)
     LCRT_HD void set_ray(float ox_, float oy_, float oz_, float dx, float dy, float dz, float oerr, float derr) {
         ox = ox_, oy = oy_, oz = oz_;
@@ -399,7 +408,7 @@ struct Traversal {
         store = store_, cb = cb_;
         tlas_nodes = tlas_nodes_, tlas_recs = tlas_recs_;
         nodes = tlas_nodes, prims = reinterpret_cast<const char *>(tlas_recs);
-        const float tmin_ = ldg16(reinterpret_cast<const f4 *>(ray)).w, tmax_ = ldg16(reinterpret_cast<const f4 *>(ray) + 1).w;
+        const float tmin_ = load_world(0).w, tmax_ = load_world(1).w;
         tmin = tmin_, tmax = tmax_;
         // the current-space ray is set up by the first step() that needs it (a single-instance TLAS goes straight to
         // its instance and never needs the world-space setup)
@@ -511,7 +520,7 @@ struct Traversal {
     // inverse when inside a non-identity instance.  One call site, so that lanes which start a ray, enter an
     // instance or return from one share the same instructions.
     LCRT_HD void setup_ray() {
-        const f4 w0 = ldg16(reinterpret_cast<const f4 *>(world)), w1 = ldg16(reinterpret_cast<const f4 *>(world) + 1);
+        const f4 w0 = load_world(0), w1 = load_world(1);
         float sox = w0.x, soy = w0.y, soz = w0.z, sdx = w1.x, sdy = w1.y, sdz = w1.z, oerr = 0.f, derr = 0.f;
         if (blas_sp >= 0 && !(cur_flags & IREC_IDENTITY)) {
             const f4 *rec = reinterpret_cast<const f4 *>(tlas_recs + store->ldw(CW_REC));

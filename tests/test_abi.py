@@ -44,6 +44,15 @@ def test_device_library_text_is_embedded():
     src = lc.device_library_source()
     assert "intersect_node8" in src and "struct alignas(16) Node8" in src
     assert "#include \"" not in src
+    # every RT name the reference's codegen can emit (cuda_codegen_ast.cpp:983-1004, 1047-1050) is defined by the text
+    for name in ("lc_accel_instance_transform", "lc_accel_instance_user_id", "lc_accel_instance_visibility_mask", "lc_accel_set_instance_transform",
+                 "lc_accel_set_instance_visibility", "lc_accel_set_instance_opacity", "lc_accel_set_instance_user_id", "lc_accel_trace_closest",
+                 "lc_accel_trace_any", "lc_accel_query_all", "lc_accel_query_any", "lc_accel_trace_closest_motion_blur",
+                 "lc_accel_trace_any_motion_blur", "lc_accel_query_all_motion_blur", "lc_accel_query_any_motion_blur", "LC_RAY_QUERY_WORLD_RAY",
+                 "LC_RAY_QUERY_PROCEDURAL_CANDIDATE_HIT", "LC_RAY_QUERY_TRIANGLE_CANDIDATE_HIT", "lc_ray_query_committed_hit",
+                 "LC_RAY_QUERY_COMMIT_TRIANGLE", "LC_RAY_QUERY_COMMIT_PROCEDURAL", "LC_RAY_QUERY_TERMINATE", "lc_ray_query_trace",
+                 "LUISA_DECL_RAY_QUERY_TRIANGLE_IMPL", "LUISA_DECL_RAY_QUERY_PROCEDURAL_IMPL", "struct alignas(16u) LCAccel"):
+        assert name in src, name
 
 
 def test_no_cpu_fallback():
