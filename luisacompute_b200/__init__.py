@@ -332,6 +332,7 @@ class Accel(_Resource):
         super().__init__(device, lib().lcbCreateAccel(device._h, C.byref(option)))
         self.option = option
         self._mods: dict[int, np.ndarray] = {}
+        self._bulk: list = []
         self._instance_count = 0
         self._prims: list = []
 
@@ -399,9 +400,11 @@ class Accel(_Resource):
         m["flags"] |= scenes.MOD_USER_ID
 
     def add_mods(self, mods: np.ndarray, instance_count: Optional[int] = None, prims=None):
-        """Bulk path: ready-made 80-byte Modification records (primitive = Mesh / ProceduralPrimitive handles)."""
-        for k in range(len(mods)):
-            self._mods[int(mods["index"][k])] = mods[k:k + 1].copy()
+        """Bulk path: ready-made 80-byte Modification records (primitive = Mesh / ProceduralPrimitive handles).  The
+        records must not repeat an instance index that already has a pending modification (the reference merges
+        per-instance modifications on the host, src/runtime/rtx/accel.cpp:75-79; a bulk batch is taken as merged)."""
+        assert mods.dtype.itemsize == 80
+        self._bulk.append(np.ascontiguousarray(mods).copy())
         if instance_count is not None:
             self._instance_count = instance_count
         if prims is not None:
@@ -411,11 +414,17 @@ class Accel(_Resource):
     def build(self, request: int = PREFER_UPDATE, update_instance_buffer_only: bool = False):
         if self._instance_count == 0:
             raise LcrtError("Building acceleration structure without instances.")
-        mods = np.zeros(len(self._mods), dtype=scenes.MOD_DTYPE)     # (np.concatenate would repack the padded 80-byte dtype)
+        nb = sum(len(b) for b in self._bulk)
+        mods = np.zeros(len(self._mods) + nb, dtype=scenes.MOD_DTYPE)     # (np.concatenate would repack the padded 80-byte dtype)
         for k, m in enumerate(self._mods.values()):
             mods[k] = m[0]
+        k = len(self._mods)
+        for b in self._bulk:
+            mods[k:k + len(b)] = b
+            k += len(b)
         assert mods.dtype.itemsize == 80 and mods.flags["C_CONTIGUOUS"]
         self._mods.clear()
+        self._bulk.clear()
         cmd = _AccelBuildCommand(self.handle, self._instance_count, request, int(update_instance_buffer_only), len(mods),
                                  mods.ctypes.data_as(C.c_void_p) if len(mods) else None)
         _check(lib().lcbAccelBuild(self.device._h, _stream(), C.byref(cmd)), "lcbAccelBuild")
