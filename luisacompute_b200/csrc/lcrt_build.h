@@ -12,6 +12,14 @@ namespace lcrt {
 #if defined(__CUDA_ARCH__)
 #define LCRT_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define LCRT_FENCE() __threadfence()
+// atomic add that releases this thread's earlier writes and acquires those released by earlier arrivals at the same
+// counter (one instruction instead of fence.sc / atom / fence.sc)
+__device__ __forceinline__ uint32_t lcrt_atomic_add_acq_rel(uint32_t *p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+#define LCRT_ATOMIC_ADD_ACQ_REL(p, v) lcrt_atomic_add_acq_rel((p), (v))
 #define LCRT_VOLATILE_LOAD_U32(p) (*reinterpret_cast<const volatile uint32_t *>(p))
 // data produced by other SMs inside the same kernel must not be served from this SM's (non-coherent) L1
 #define LCRT_LOAD_CG_F4(p) __ldcg(reinterpret_cast<const float4 *>(p))
@@ -22,6 +30,7 @@ inline uint32_t host_atomic_add(uint32_t *p, uint32_t v) {
     return o;
 }
 #define LCRT_ATOMIC_ADD(p, v) ::lcrt::host_atomic_add((p), (v))
+#define LCRT_ATOMIC_ADD_ACQ_REL(p, v) ::lcrt::host_atomic_add((p), (v))
 #define LCRT_FENCE() ((void)0)
 #define LCRT_VOLATILE_LOAD_U32(p) (*(p))
 #define LCRT_LOAD_CG_F4(p) (*(p))
@@ -252,9 +261,7 @@ LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
             parent = left - 1u, from_left = false;
             t.child[parent].y = cur, t.range[parent].y = right;
         }
-        LCRT_FENCE();
-        if (LCRT_ATOMIC_ADD(&t.flag[parent], 1u) == 0u) return;// the sibling will finish this node
-        LCRT_FENCE();
+        if (LCRT_ATOMIC_ADD_ACQ_REL(&t.flag[parent], 1u) == 0u) return;// the sibling will finish this node
         // second arrival: merge with the sibling
         const uint32_t sib = LCRT_VOLATILE_LOAD_U32(from_left ? &t.child[parent].y : &t.child[parent].x);
         if (from_left) right = LCRT_VOLATILE_LOAD_U32(&t.range[parent].y);
@@ -280,31 +287,66 @@ struct Bvh8Out {
     char *prims;
     uint32_t *parent;     // optional (allow_update): (parent << 3) | slot
     uint32_t *task;       // [node_capacity] bvh2 node id per wide node, INVALID until scheduled
+    uint32_t *rec_src;    // [prim_count] sorted position whose primitive goes into record j (records are written by a
+                          // separate, fully parallel pass: emit_record)
     uint32_t *counters;   // [0] nodes allocated, [1] prims allocated, [2] prims finished
     uint32_t node_capacity;
 };
 
+// Quantisation of child boxes onto the node's 8-bit grid: origin p = node lo, per-axis step 2^(e-127) with e the
+// smallest exponent for which 255 steps span the node, child lo rounded down and hi rounded up.  The host evaluates
+// the differences exactly in double; the device uses fp32 with directed rounding — floor(fl_down(lo - p) * 2^-k) equals
+// floor((lo - p) * 2^-k) because every grid line n * 2^k is itself a float (DESIGN.md "quantisation"), so both produce
+// the same bytes.
+LCRT_HD uint32_t quant_exponent(float lo, float hi) {// biased exponent e, 0 for an empty / degenerate extent
+#if defined(__CUDA_ARCH__)
+    const float ext = __fsub_ru(hi, lo);
+#else
+    const double ext = (double)hi - (double)lo;
+#endif
+    if (!(ext > 0)) return 0u;
+    int ex;
+#if defined(__CUDA_ARCH__)
+    const float m = frexpf(ext, &ex);// ext = m * 2^ex, m in [0.5, 1)
+    int ee = (m <= 0.99609375f ? ex - 8 : ex - 7) + 127;// 255 * 2^(e-127) >= ext  <=>  m * 2^(ex-k) <= 255/256 * 2^8
+#else
+    const double m = frexp(ext, &ex);
+    int ee = (m <= 0.99609375 ? ex - 8 : ex - 7) + 127;
+#endif
+    if (ee < 1) ee = 1;
+    if (ee > 254) ee = 254;
+    return (uint32_t)ee;
+}
+LCRT_HD uint32_t quant_down(float x, float p, uint32_t e) {
+    if (e == 0u) return 0u;
+#if defined(__CUDA_ARCH__)
+    float q = floorf(__fsub_rd(x, p) * as_float((254u - e) << 23));// 2^-(e-127), exact scaling
+#else
+    double q = floor(((double)x - (double)p) * ldexp(1.0, 127 - (int)e));
+#endif
+    if (!(q >= 0)) q = 0;
+    if (q > 255) q = 255;
+    return (uint32_t)q;
+}
+LCRT_HD uint32_t quant_up(float x, float p, uint32_t e) {
+    if (e == 0u) return 0u;
+#if defined(__CUDA_ARCH__)
+    float q = ceilf(__fsub_ru(x, p) * as_float((254u - e) << 23));
+#else
+    double q = ceil(((double)x - (double)p) * ldexp(1.0, 127 - (int)e));
+#endif
+    if (!(q >= 0)) q = 0;
+    if (q > 255) q = 255;
+    return (uint32_t)q;
+}
+
 LCRT_HD void quantize_node(Node8 &nd, const Box &nb, const Box *cb, const bool *valid) {
     float p[3];
     uint32_t eb[3];
-    double scale[3];
     for (int a = 0; a < 3; a++) {
         const bool ok = nb.lo[a] <= nb.hi[a];// false for empty / NaN bounds
         p[a] = ok ? nb.lo[a] : 0.f;
-        const double ext = ok ? (double)nb.hi[a] - (double)nb.lo[a] : 0.0;
-        uint32_t e = 0u;
-        if (ext > 0.0) {
-            int ex;
-            // smallest e with 255 * 2^(e-127) >= ext
-            const double m = frexp(ext / 255.0, &ex);// ext/255 = m * 2^ex, m in [0.5, 1)
-            int ee = (m == 0.5) ? ex - 1 : ex;
-            ee += 127;
-            if (ee < 1) ee = 1;
-            if (ee > 254) ee = 254;
-            e = (uint32_t)ee;
-        }
-        eb[a] = e;
-        scale[a] = e ? ldexp(1.0, (int)e - 127) : 0.0;
+        eb[a] = ok ? quant_exponent(nb.lo[a], nb.hi[a]) : 0u;
     }
     nd.px = p[0], nd.py = p[1], nd.pz = p[2];
     nd.ex = (uint8_t)eb[0], nd.ey = (uint8_t)eb[1], nd.ez = (uint8_t)eb[2];
@@ -313,19 +355,7 @@ LCRT_HD void quantize_node(Node8 &nd, const Box &nb, const Box *cb, const bool *
     for (int s = 0; s < 8; s++) {
         for (int a = 0; a < 3; a++) {
             uint32_t ql = 255u, qh = 0u;// inverted: never hit
-            if (valid[s] && cb[s].lo[a] <= cb[s].hi[a]) {
-                if (scale[a] > 0.0) {
-                    double l = floor(((double)cb[s].lo[a] - (double)p[a]) / scale[a]);
-                    double h = ceil(((double)cb[s].hi[a] - (double)p[a]) / scale[a]);
-                    if (l < 0.0) l = 0.0;
-                    if (l > 255.0) l = 255.0;
-                    if (h < 0.0) h = 0.0;
-                    if (h > 255.0) h = 255.0;
-                    ql = (uint32_t)l, qh = (uint32_t)h;
-                } else {
-                    ql = 0u, qh = 0u;
-                }
-            }
+            if (valid[s] && cb[s].lo[a] <= cb[s].hi[a]) ql = quant_down(cb[s].lo[a], p[a], eb[a]), qh = quant_up(cb[s].hi[a], p[a], eb[a]);
             qlo[a][s] = (uint8_t)ql, qhi[a][s] = (uint8_t)qh;
         }
     }
@@ -476,8 +506,7 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
         } else {
             uint32_t pos[4];
             const uint32_t cnt = gather_leaf(t, cid[k], pos, 3u);
-            for (uint32_t q = 0; q < cnt; q++)
-                in.write(o.prims + (uint64_t)(prim_base + po + q) * Input::rec_bytes, t.order[pos[q]]);
+            for (uint32_t q = 0; q < cnt; q++) o.rec_src[prim_base + po + q] = pos[q];
             const uint32_t unary = cnt == 1u ? 1u : cnt == 2u ? 3u : 7u;
             nd.meta[s] = (uint8_t)((unary << 5) | po);
             po += cnt;
@@ -489,9 +518,16 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
         for (int a = 0; a < 3; a++) o.header->lo[a] = nb.lo[a], o.header->hi[a] = nb.hi[a];
         if (o.parent) o.parent[0] = INVALID_U32;
     }
-    LCRT_FENCE();// tasks, parents and records are visible before the completion counter moves
-    if (n_prims) LCRT_ATOMIC_ADD(&o.counters[2], n_prims);
+    // tasks and parents are released before the completion counter moves
+    if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2], n_prims);
+    else LCRT_FENCE();
     return true;
+}
+
+// record j of the blob <- primitive order[rec_src[j]] (one thread per record)
+template<class Input>
+LCRT_HD void emit_record(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t j) {
+    in.write(o.prims + (uint64_t)j * Input::rec_bytes, t.order[o.rec_src[j]]);
 }
 
 // ------------------------------------------------------------------------------------------ refit
@@ -555,10 +591,8 @@ LCRT_HD void refit_climb(const RefitCtx &c, const Input &in, uint32_t widx) {
         refit_node(c, in, cur);
         if (cur == 0u) return;
         const uint32_t p = c.parent[cur] >> 3;
-        LCRT_FENCE();
         const uint32_t need = (uint32_t)popc(c.nodes[p].imask);
-        if (LCRT_ATOMIC_ADD(&c.arrived[p], 1u) + 1u < need) return;
-        LCRT_FENCE();
+        if (LCRT_ATOMIC_ADD_ACQ_REL(&c.arrived[p], 1u) + 1u < need) return;
         cur = p;
     }
 }

@@ -30,7 +30,7 @@ static_assert(SORT_TILE == SORT_TILE_KEYS, "lcrt_layout.h and lcrt_sort.cuh disa
 // =====================================================================================================================
 // build kernels
 // =====================================================================================================================
-enum SmallSlots : uint32_t { SM_CMIN = 0, SM_CMAX = 3, SM_ROOT = 6, SM_ABORT = 7, SM_COUNTERS = 8 /* nodes, prims, done */ };
+enum SmallSlots : uint32_t { SM_CMIN = 0, SM_CMAX = 3, SM_ROOT = 6, SM_ABORT = 7, SM_COUNTERS = 8 /* nodes, prims, done */, SM_BARRIER = 11 /* arrivals, generation, node-count snapshots [2] */ };
 
 __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t flags, BlobLayout L, uint32_t *small) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -45,6 +45,7 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
         small[SM_CMAX + 0] = small[SM_CMAX + 1] = small[SM_CMAX + 2] = 0u;
         small[SM_ROOT] = INVALID_U32, small[SM_ABORT] = 0u;
         small[SM_COUNTERS + 0] = 1u, small[SM_COUNTERS + 1] = 0u, small[SM_COUNTERS + 2] = 0u;
+        small[SM_BARRIER + 0] = small[SM_BARRIER + 1] = small[SM_BARRIER + 2] = small[SM_BARRIER + 3] = 0u;
         if (n == 0u) {
             // an empty structure: one node with no children; nothing can be hit
             Node8 nd;
@@ -117,35 +118,57 @@ __global__ void __launch_bounds__(256) k_climb(Bvh2 t, Input in) {
     if (i < t.n) lbvh_climb(t, i, in.box(t.order[i]));
 }
 
-// Persistent work queue: wide node w is built from binary subtree task[w]; children are appended with atomicAdd and
-// their tasks published before the completion counter moves.  The grid never exceeds what is co-resident, so a
-// polling thread can not starve the thread that will publish its task.
+#ifndef LCRT_COLLAPSE_MIN_BLOCKS
+#define LCRT_COLLAPSE_MIN_BLOCKS 4
+#endif
+// BVH2 -> BVH8, level by level inside ONE persistent kernel: the wide nodes of a level are the contiguous index range
+// allocated while the previous level was processed, so each level is a grid-stride loop over [begin, end) followed by
+// a grid-wide barrier (arrival counter + generation word; the last block to arrive snapshots the node counter, which
+// is the next level's `end`).  The grid never exceeds what is co-resident, so the barrier can not deadlock; a level
+// costs one node latency plus ~2 us, there is no polling on individual tasks.
 template<class Input>
-__global__ void __launch_bounds__(128) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag) {
-    const uint32_t stride = gridDim.x * blockDim.x;
-    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t polls = 0;
-    while (w < o.node_capacity) {
-        uint32_t bid = (w == 0u) ? *t.root : LCRT_VOLATILE_LOAD_U32(&o.task[w]);
-        if (bid == INVALID_U32) {
-            if (LCRT_VOLATILE_LOAD_U32(&o.counters[2]) >= t.n || LCRT_VOLATILE_LOAD_U32(abort_flag) != 0u) {
-                bid = LCRT_VOLATILE_LOAD_U32(&o.task[w]);// published before the counter moved?
-                if (bid == INVALID_U32) break;
+__global__ void __launch_bounds__(128, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *bar) {
+    const uint32_t stride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_end;
+    uint32_t begin = 0u, end = 1u, gen = 0u;
+    while (begin < end) {
+        for (uint32_t w = begin + gtid; w < end; w += stride) {
+            const uint32_t bid = (w == 0u) ? *t.root : LCRT_VOLATILE_LOAD_U32(&o.task[w]);
+            if (bid == INVALID_U32 || !collapse_node(t, o, in, w, bid)) atomicExch(abort_flag, 1u);
+        }
+        // ---- grid barrier
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&bar[0], 1u) == gridDim.x * (gen + 1u) - 1u) {
+                const uint32_t count = LCRT_VOLATILE_LOAD_U32(&o.counters[0]);
+                bar[2 + (gen & 1u)] = LCRT_VOLATILE_LOAD_U32(abort_flag) ? end : (count < o.node_capacity ? count : o.node_capacity);
+                __threadfence();
+                atomicExch(&bar[1], gen + 1u);
             } else {
-                if (++polls > (1u << 24)) {// safety net: never hang the device
-                    atomicExch(abort_flag, 2u);
-                    break;
+                uint32_t polls = 0u;
+                while (LCRT_VOLATILE_LOAD_U32(&bar[1]) <= gen) {
+                    __nanosleep(20);
+                    if (++polls > (1u << 24)) {// safety net (never reached with a cooperative launch): give up, never hang
+                        atomicExch(abort_flag, 2u);
+                        break;
+                    }
                 }
-                __nanosleep(64);
-                continue;
             }
+            __threadfence();
+            s_end = LCRT_VOLATILE_LOAD_U32(abort_flag) == 2u ? end : LCRT_VOLATILE_LOAD_U32(&bar[2 + (gen & 1u)]);
         }
-        if (!collapse_node(t, o, in, w, bid)) {
-            atomicExch(abort_flag, 1u);
-            break;
-        }
-        w += stride;
+        __syncthreads();
+        gen++;
+        begin = end, end = s_end;
+        __syncthreads();
     }
+}
+
+template<class Input>
+__global__ void __launch_bounds__(256) k_emit_records(Bvh2 t, Bvh8Out o, Input in) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < t.n) emit_record(t, o, in, j);
 }
 
 __global__ void k_build_finalize(BlobHeader *h, const uint32_t *small, uint32_t n) {
@@ -472,6 +495,7 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     o.header = h, o.nodes = reinterpret_cast<Node8 *>(bp + L.nodes_offset), o.prims = bp + L.prims_offset;
     o.parent = L.parent_offset ? reinterpret_cast<uint32_t *>(bp + L.parent_offset) : nullptr;
     o.task = task, o.counters = small + SM_COUNTERS, o.node_capacity = L.node_capacity;
+    o.rec_src = sb.vals[cur ^ 1];// the idle half of the sort's ping-pong buffers
     {
         int &bps = dev->collapse_blocks_per_sm[Input::kind];
         if (bps == 0) {
@@ -481,9 +505,14 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
         uint32_t g = (uint32_t)(dev->sm_count * bps);
         const uint32_t need = (L.node_capacity + 127u) / 128u;
         if (g > need) g = need;
-        k_collapse<Input><<<g, 128, 0, stream>>>(t, o, in, small + SM_ABORT);
-        LCRT_LAUNCH_CHECK("k_collapse");
+        // cooperative launch: the runtime guarantees that all blocks are co-resident (the kernel has a grid barrier)
+        uint32_t *abort_flag = small + SM_ABORT, *bar = small + SM_BARRIER;
+        Input in_arg = in;
+        void *args[] = {&t, &o, &in_arg, &abort_flag, &bar};
+        LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(128), args, 0, stream));
     }
+    k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in);
+    LCRT_LAUNCH_CHECK("k_emit_records");
     k_build_finalize<<<1, 32, 0, stream>>>(h, small, n);
     LCRT_LAUNCH_CHECK("k_build_finalize");
     return LCRT_SUCCESS;

@@ -82,14 +82,19 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
     if (root == INVALID_U32) return -10;
     std::vector<uint32_t> task(L.node_capacity, INVALID_U32);
     uint32_t counters[3] = {1u, 0u, 0u};
+    std::vector<uint32_t> rec_src(n, INVALID_U32);
     Bvh8Out o{h, nodes, blob + L.prims_offset, L.parent_offset ? reinterpret_cast<uint32_t *>(blob + L.parent_offset) : nullptr, task.data(),
-              counters, L.node_capacity};
+              rec_src.data(), counters, L.node_capacity};
     task[0] = root;
     for (uint32_t w = 0; w < counters[0]; w++) {
         if (task[w] == INVALID_U32) return -11;
         if (!collapse_node(t, o, in, w, task[w])) return -12;
     }
     if (counters[2] != n || counters[1] != n) return -13;
+    for (uint32_t j = 0; j < n; j++) {
+        if (rec_src[j] == INVALID_U32) return -14;
+        emit_record(t, o, in, j);
+    }
     h->node_count = counters[0], h->prim_written = counters[1], h->built = 1;
     return 0;
 }
