@@ -350,7 +350,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * reps * 2 * n / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": 2 * n * 24,
                "ms_per_step": dt / reps * 1e3, "api": "Accel.trace_closest_host -> lcbTraceClosestHost (pinned host rays in, pinned host hits out, "
-               "512Ki-ray chunks double-buffered over two streams)"}
+               "512Ki-ray chunks, four in flight on four streams)"}
         # the host path must return exactly what the resident path returned
         assert torch.equal(h_hits[:n], d_hits_p.cpu()) and torch.equal(h_hits[n:], d_hits_b.cpu())
 

@@ -99,7 +99,7 @@ LCRT_API int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, cons
                       uint32_t mask, int terminate_on_first, uint32_t tri_program, uint32_t proc_program, void *hits);
 
 /* Host-buffer convenience (the end-to-end path bench.py times as `e2e`): rays in pinned host memory -> chunked,
- * double-buffered H2D copy / trace / D2H copy on internal streams -> hits in pinned host memory.  Synchronous. */
+ * pipelined (four chunks in flight) H2D copy / trace / D2H copy on internal streams -> hits in pinned host memory.  Synchronous. */
 LCRT_API int lcbTraceClosestHost(lcbDevice *device, uint64_t accel, const void *host_rays, uint64_t ray_count, uint32_t mask,
                                  void *host_hits, uint64_t chunk_rays);
 

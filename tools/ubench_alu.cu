@@ -55,6 +55,16 @@ __global__ void __launch_bounds__(1024) k(uint32_t *out, uint32_t seed, long lon
                 if (OP == 27) asm volatile("{.reg .pred q; setp.le.f32 q, %0, %1; selp.f32 %0, %2, %0, q;}" : "+f"(f[i]) : "f"(fa), "f"(fb));
                 if (OP == 28) asm volatile("{.reg .b32 t; bfind.u32 t, %0; add.u32 %0, %0, t;}" : "+r"(r[i]));
                 if (OP == 29) asm volatile("{.reg .b32 t; popc.b32 t, %0; add.u32 %0, %0, t;}" : "+r"(r[i]));
+                if (OP == 31) asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(seed), "r"(seed));
+                if (OP == 32) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb)); asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(seed), "r"(seed)); }
+                if (OP == 33) { asm volatile("prmt.b32 %0, %0, %1, 0x7144;" : "+r"(r[i]) : "r"(seed)); asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(r[(i+4)%CHAINS]) : "r"(seed), "r"(seed)); }
+                if (OP == 34) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb)); asm volatile("prmt.b32 %0, %0, %1, 0x7144;" : "+r"(r[i]) : "r"(seed)); asm volatile("dp4a.u32.u32 %0, %0, %1, %2;" : "+r"(r[(i+4)%CHAINS]) : "r"(seed), "r"(seed));}
+                if (OP == 35) { asm volatile("prmt.b32 %0, %0, %1, 0x7144;" : "+r"(r[i]) : "r"(seed)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[(i+4)%CHAINS]) : "r"(seed), "r"(seed)); }
+                if (OP == 36) { asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb)); asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(r[i]) : "r"(seed), "r"(seed)); }
+                if (OP == 37) { asm volatile("max.f32 %0, %0, %1;" : "+f"(f[i]) : "f"(fa)); asm volatile("prmt.b32 %0, %0, %1, 0x7144;" : "+r"(r[i]) : "r"(seed)); }
+                if (OP == 38) { asm volatile("max.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[(i+4)%CHAINS]) : "f"(fa), "f"(fb)); }
+                if (OP == 39) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb)); asm volatile("prmt.b32 %0, %0, %1, 0x7144;" : "+r"(r[i]) : "r"(seed)); }
+                if (OP == 40) { asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(p[i]) : "l"(pa), "l"(pb)); asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(f[i]) : "f"(fa), "f"(fb)); }
                 if (OP == 30) asm volatile("{.reg .pred q; setp.le.f32 q, %0, %1; @q mov.f32 %0, %2;}" : "+f"(f[i]) : "f"(fa), "f"(fb));
             }
         }
@@ -119,6 +129,16 @@ int main() {
         run<28>("BFIND+IADD", threads);
         run<29>("POPC+IADD", threads);
         run<30>("FSETP+@p MOV", threads);
+        run<31>("IDP4A", threads);
+        run<32>("FFMA + IDP4A pair", threads);
+        run<33>("PRMT + IDP4A pair", threads);
+        run<34>("FFMA2 + PRMT + IDP4A triple", threads);
+        run<35>("PRMT + IMAD pair", threads);
+        run<36>("FFMA + IMAD pair", threads);
+        run<37>("FMNMX + PRMT pair", threads);
+        run<38>("FMNMX3 + FFMA pair", threads);
+        run<39>("FFMA2 + PRMT pair", threads);
+        run<40>("FFMA2 + FFMA pair", threads);
     }
     return 0;
 }
