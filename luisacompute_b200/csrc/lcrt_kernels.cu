@@ -233,11 +233,26 @@ __global__ void k_update_handles(Instance *instances, const InstanceHandleUpdate
 // =====================================================================================================================
 // trace kernels
 // =====================================================================================================================
-constexpr int TRACE_BLOCK = 128;
+#ifndef LCRT_TRACE_BLOCK
+#define LCRT_TRACE_BLOCK 128
+#endif
+constexpr int TRACE_BLOCK = LCRT_TRACE_BLOCK;
 constexpr int TRACE_SMEM_STACK = 8;   // stack entries per thread kept in shared memory
 constexpr uint32_t TRACE_BATCH = 128; // rays a warp reserves per atomic
 #ifndef LCRT_TRACE_MIN_BLOCKS
 #define LCRT_TRACE_MIN_BLOCKS 5     // resident blocks per SM the register allocation is bounded for
+#endif
+#ifndef LCRT_TRI_VOTE
+#define LCRT_TRI_VOTE 4               // lanes with a pending primitive that make the warp run the primitive phase
+#endif
+#ifndef LCRT_DEFER_PRIMS
+#define LCRT_DEFER_PRIMS 0            // park hit leaf slots and go on with nodes (Traversal::DEFER)
+#endif
+#ifndef LCRT_STREAM_HITS
+#define LCRT_STREAM_HITS 1
+#endif
+#ifndef LCRT_PREFETCH_RAYS
+#define LCRT_PREFETCH_RAYS 1
 #endif
 #ifndef LCRT_REFILL_MIN
 #define LCRT_REFILL_MIN 12            // idle lanes that trigger a warp-cooperative refill
@@ -258,6 +273,7 @@ __device__ __forceinline__ TraceSmem *trace_smem() {
 }
 struct HybridStore {
     static constexpr bool world_in_global = true;
+    static constexpr bool defer_prims = LCRT_DEFER_PRIMS != 0;
     u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
     __device__ __forceinline__ void store(int i, u2 v) {
         if (i < TRACE_SMEM_STACK) trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] = v;
@@ -318,7 +334,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                 const bool hit = tr.has_hit();
                 if constexpr (MODE == MODE_CLOSEST) {
                     u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
+#if LCRT_STREAM_HITS
+                    __stcs(reinterpret_cast<uint2 *>(o), make_uint2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u));
+                    __stcs(reinterpret_cast<uint2 *>(o) + 1, make_uint2(hit ? tr.hit_rec() : 0u, 0u));
+                    __stcs(reinterpret_cast<uint2 *>(o) + 2, make_uint2(as_uint(tr.hit_t()), 0u));
+#else
                     o[0] = make_u2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u), o[1] = make_u2(hit ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(as_uint(tr.hit_t()), 0u);
+#endif
                 } else if constexpr (MODE == MODE_ANY) {
                     static_cast<uint32_t *>(p.out)[ray_idx] = hit ? 1u : 0u;
                 } else {
@@ -338,6 +360,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                 base = __shfl_sync(0xffffffffu, base, 0);
                 warp_next = base < p.n ? base : p.n;
                 warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
+#if LCRT_PREFETCH_RAYS
+                // the reserved rays (TRACE_BATCH x 32 B = one 128-byte line per lane) stream from HBM exactly once
+                if (warp_next + lane * 4u < warp_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rays + warp_next + lane * 4u));
+#endif
                 if (warp_next == warp_end) exhausted = true;
             }
             const uint64_t avail = warp_end - warp_next;
@@ -350,8 +376,20 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
             }
             warp_next += want < avail ? want : avail;
         }
-        // ---- one traversal step per lane
-        if (active && !tr.step()) active = false, unsaved = true;
+        // ---- one traversal step per lane: a node, then (if the warp votes for it) a primitive
+        bool alive = active && tr.step_node();
+#if LCRT_TRI_VOTE > 0
+        {
+            // the primitive phase runs at a few lanes per warp when every lane enters it as soon as it has a candidate;
+            // lanes with a pending primitive wait until LCRT_TRI_VOTE of them (or every live lane) can go together
+            const uint32_t am = __ballot_sync(0xffffffffu, alive);
+            const uint32_t pm = __ballot_sync(0xffffffffu, alive && tr.prim_pending());
+            if ((uint32_t)__popc(pm) >= (uint32_t)LCRT_TRI_VOTE || pm == am) alive = alive && tr.step_prim(true);
+        }
+#else
+        alive = alive && tr.step_prim(false);
+#endif
+        if (active && !alive) active = false, unsaved = true;
     }
     if constexpr (COUNT) {
 #pragma unroll

@@ -240,17 +240,36 @@ int hs_validate(const void *blob_, uint64_t *stats) {
 }
 
 // ---- tracing with the device traversal code -----------------------------------------------------------------
-void hs_trace_closest(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
-                      void *hits_, uint64_t *counters) {
+// schedule of the two step halves: 0 = step() as the inline entry points do, 1 = primitive deferral with the
+// `join` argument toggled pseudo-randomly (what a warp vote looks like from one lane)
+static int g_defer = 0;
+void hs_set_defer(int on) { g_defer = on; }
+extern "C++" template<class Tr>
+void run_ray(Tr &tr, uint64_t i) {
+    if (!Tr::DEFER) {
+        while (tr.step()) {}
+        return;
+    }
+    uint32_t lcg = (uint32_t)i * 2654435761u + 12345u;
+    while (tr.step_node()) {
+        lcg = lcg * 1664525u + 1013904223u;
+        const bool vote = (lcg >> 29) < 3u;
+        if ((tr.prim_pending() || vote) && !tr.step_prim(vote)) break;
+    }
+}
+
+extern "C++" template<class St>
+void trace_closest_impl(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
+                               void *hits_, uint64_t *counters) {
     const Ray *rays = static_cast<const Ray *>(rays_);
     SurfaceHit *hits = static_cast<SurfaceHit *>(hits_);
     uint64_t cn = 0, cp = 0, ci = 0, ce = 0;
     for (uint64_t i = 0; i < n; i++) {
-        LocalStore st;
+        St st;
         NoCallbacks cb;
-        Traversal<MODE_CLOSEST, true, LocalStore, NoCallbacks> tr;
+        Traversal<MODE_CLOSEST, true, St, NoCallbacks> tr;
         tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
-        while (tr.step()) {}
+        run_ray(tr, i);
         SurfaceHit h;
         uint32_t type;
         tr.result(h.inst, h.prim, type, h.t, h.u, h.v);
@@ -261,35 +280,51 @@ void hs_trace_closest(const void *tlas, const void *instances, const void *rays_
     }
     if (counters) counters[0] = cn, counters[1] = cp, counters[2] = ci, counters[3] = ce;
 }
+void hs_trace_closest(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
+                      void *hits_, uint64_t *counters) {
+    if (g_defer) trace_closest_impl<LocalStoreDefer>(tlas, instances, rays_, n, masks, mask_stride, hits_, counters);
+    else trace_closest_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, hits_, counters);
+}
 
-void hs_trace_any(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, uint32_t *out) {
+extern "C++" template<class St>
+void trace_any_impl(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, uint32_t *out) {
     const Ray *rays = static_cast<const Ray *>(rays_);
     for (uint64_t i = 0; i < n; i++) {
-        LocalStore st;
+        St st;
         NoCallbacks cb;
-        Traversal<MODE_ANY, false, LocalStore, NoCallbacks> tr;
+        Traversal<MODE_ANY, false, St, NoCallbacks> tr;
         tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
-        while (tr.step()) {}
+        run_ray(tr, i);
         out[i] = tr.has_hit() ? 1u : 0u;
     }
 }
+void hs_trace_any(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, uint32_t *out) {
+    if (g_defer) trace_any_impl<LocalStoreDefer>(tlas, instances, rays_, n, masks, mask_stride, out);
+    else trace_any_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, out);
+}
 
-void hs_query(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
-              int terminate_on_first, uint32_t tri_prog, uint32_t proc_prog, void *hits_) {
+extern "C++" template<class St>
+void query_impl(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
+                       int terminate_on_first, uint32_t tri_prog, uint32_t proc_prog, void *hits_) {
     const Ray *rays = static_cast<const Ray *>(rays_);
     CommittedHit *hits = static_cast<CommittedHit *>(hits_);
     for (uint64_t i = 0; i < n; i++) {
-        LocalStore st;
+        St st;
         BuiltinPrograms cb{tri_prog, proc_prog};
-        Traversal<MODE_QUERY, false, LocalStore, BuiltinPrograms> tr;
+        Traversal<MODE_QUERY, false, St, BuiltinPrograms> tr;
         tr.init(static_cast<const BlobHeader *>(tlas), static_cast<const Instance *>(instances), &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
         tr.terminate_on_first = terminate_on_first != 0;
-        while (tr.step()) {}
+        run_ray(tr, i);
         CommittedHit h;
         tr.result(h.inst, h.prim, h.hit_type, h.t, h.u, h.v);
         if (h.hit_type == HIT_MISS) h.t = rays[i].tmax;
         hits[i] = h;
     }
+}
+void hs_query(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
+              int terminate_on_first, uint32_t tri_prog, uint32_t proc_prog, void *hits_) {
+    if (g_defer) query_impl<LocalStoreDefer>(tlas, instances, rays_, n, masks, mask_stride, terminate_on_first, tri_prog, proc_prog, hits_);
+    else query_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, terminate_on_first, tri_prog, proc_prog, hits_);
 }
 
 }// extern "C"

@@ -43,6 +43,7 @@ def lib():
         L.hs_trace_closest.argtypes = [vp, vp, vp, u64, vp, ci, vp, vp]
         L.hs_trace_any.argtypes = [vp, vp, vp, u64, vp, ci, vp]
         L.hs_query.argtypes = [vp, vp, vp, u64, vp, ci, ci, u32, u32, vp]
+        L.hs_set_defer.argtypes = [ci]
         _LIB = L
     return _LIB
 

@@ -10,6 +10,15 @@ from luisacompute_b200 import scenes as S
 from tests.hostsim import hostsim_py as H
 
 
+@pytest.fixture(autouse=True, params=[0, 1], ids=["inline", "deferred"])
+def schedule(request):
+    """Both schedules of the traversal: step() as the inline entry points run it, and the batch kernel's primitive
+    deferral with a pseudo-random vote."""
+    H.lib().hs_set_defer(request.param)
+    yield request.param
+    H.lib().hs_set_defer(0)
+
+
 def _pair(oracle, meshes, affines, blas_index=None, masks=None, opaque=None, user_ids=None, flags=0):
     """Build the same scene in the oracle and in the host simulation."""
     blas_index = list(range(len(affines))) if blas_index is None else blas_index
