@@ -72,6 +72,9 @@ typedef struct lcbAccelBinding {
 LCRT_API lcbDevice *lcbDeviceCreate(int device_index);
 LCRT_API void lcbDeviceDestroy(lcbDevice *device);
 LCRT_API const char *lcbBackendName(void);
+/* backend_device_names (cuda_device.cpp:1213-1228): CUDA devices this process can see, 0 without a GPU */
+LCRT_API int lcbDeviceCount(void);
+LCRT_API int lcbDeviceName(int device_index, char *name, int capacity);
 
 LCRT_API uint64_t lcbCreateMesh(lcbDevice *device, const lcbAccelOption *option);
 LCRT_API void lcbDestroyMesh(lcbDevice *device, uint64_t handle);
@@ -114,6 +117,24 @@ LCRT_API int lcbSynchronize(lcbDevice *device, lcrtStream stream);
 LCRT_API int lcbDownload(lcbDevice *device, lcrtStream stream, uint64_t device_address, void *host, uint64_t bytes);
 LCRT_API int lcbUpload(lcbDevice *device, lcrtStream stream, uint64_t device_address, const void *host, uint64_t bytes);
 
+/* Plumbing the backend plugin (plugin/lc_backend_b200rt.cpp) builds DeviceInterface's buffer / stream / event methods
+ * from, so that the plugin contains no CUDA calls: replaces CUDADevice::create_buffer / create_stream / create_event
+ * (src/backends/cuda/cuda_device.cpp:281-340, 460-480, 985-1020), CUDAStream (cuda_stream.cpp:142-199: host callbacks run
+ * after the GPU work queued before them) and CUDAEvent (cuda_event.cpp: timeline semaphore with fence values).
+ * A buffer handle IS its device address (~0 on failure). */
+typedef struct lcbEvent lcbEvent;
+LCRT_API uint64_t lcbBufferCreate(lcbDevice *device, uint64_t bytes);
+LCRT_API void lcbBufferDestroy(lcbDevice *device, uint64_t address);
+LCRT_API lcrtStream lcbStreamCreate(lcbDevice *device);
+LCRT_API void lcbStreamDestroy(lcbDevice *device, lcrtStream stream);
+LCRT_API int lcbCopyAsync(lcbDevice *device, lcrtStream stream, void *dst, const void *src, uint64_t bytes);
+LCRT_API int lcbHostCallback(lcbDevice *device, lcrtStream stream, void (*fn)(void *), void *user);
+LCRT_API lcbEvent *lcbEventCreate(lcbDevice *device);
+LCRT_API void lcbEventDestroy(lcbDevice *device, lcbEvent *event);
+LCRT_API int lcbEventSignal(lcbDevice *device, lcbEvent *event, lcrtStream stream, uint64_t value);
+LCRT_API int lcbEventWait(lcbDevice *device, lcbEvent *event, lcrtStream stream, uint64_t value);
+LCRT_API int lcbEventSynchronize(lcbDevice *device, lcbEvent *event, uint64_t value);
+LCRT_API int lcbEventIsCompleted(lcbDevice *device, lcbEvent *event, uint64_t value);
 #ifdef __cplusplus
 }
 #endif

@@ -321,6 +321,18 @@ extern "C" {
 
 const char *lcbBackendName(void) { return "b200rt"; }
 
+int lcbDeviceCount(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+
+int lcbDeviceName(int device_index, char *name, int capacity) {
+    cudaDeviceProp prop;
+    if (name == nullptr || capacity <= 0 || cudaGetDeviceProperties(&prop, device_index) != cudaSuccess) return LCRT_ERROR_INVALID_VALUE;
+    snprintf(name, (size_t)capacity, "%s", prop.name);
+    return 0;
+}
+
 lcbDevice *lcbDeviceCreate(int device_index) {
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
@@ -524,6 +536,112 @@ int lcbUpload(lcbDevice *device, lcrtStream stream, uint64_t device_address, con
     LCB_CUDA(cudaMemcpyAsync(reinterpret_cast<void *>(device_address), host, bytes, cudaMemcpyHostToDevice, static_cast<cudaStream_t>(stream)));
     LCB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
     return 0;
+}
+
+// ---- plumbing for the backend plugin (plugin/lc_backend_b200rt.cpp): device memory, streams, copies, host callbacks
+// and timeline events, so that the plugin itself contains no CUDA calls (cuda_device.cpp:281-340, cuda_stream.cpp,
+// cuda_event.cpp are what it stands in for)
+uint64_t lcbBufferCreate(lcbDevice *device, uint64_t bytes) {
+    if (!device) return ~0ull;
+    cudaSetDevice(device->index);
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) return ~0ull;
+    return reinterpret_cast<uint64_t>(p);
+}
+void lcbBufferDestroy(lcbDevice *device, uint64_t address) {
+    if (!device || address == ~0ull) return;
+    cudaSetDevice(device->index);
+    cudaFree(reinterpret_cast<void *>(address));
+}
+lcrtStream lcbStreamCreate(lcbDevice *device) {
+    if (!device) return nullptr;
+    cudaSetDevice(device->index);
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+    return s;
+}
+void lcbStreamDestroy(lcbDevice *device, lcrtStream stream) {
+    if (!device || !stream) return;
+    cudaSetDevice(device->index);
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaStreamDestroy(static_cast<cudaStream_t>(stream));
+}
+int lcbCopyAsync(lcbDevice *device, lcrtStream stream, void *dst, const void *src, uint64_t bytes) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+    return 0;
+}
+int lcbHostCallback(lcbDevice *device, lcrtStream stream, void (*fn)(void *), void *user) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaLaunchHostFunc(static_cast<cudaStream_t>(stream), fn, user));
+    return 0;
+}
+// timeline event: signal(value) records a CUDA event tagged with the fence value, wait / synchronise use the first
+// recorded event whose value is >= the one asked for
+struct lcbEvent {
+    std::mutex mutex;
+    std::vector<std::pair<uint64_t, cudaEvent_t>> signals;
+};
+lcbEvent *lcbEventCreate(lcbDevice *device) { return device ? new lcbEvent{} : nullptr; }
+void lcbEventDestroy(lcbDevice *device, lcbEvent *event) {
+    if (!device || !event) return;
+    cudaSetDevice(device->index);
+    for (auto &s : event->signals) cudaEventDestroy(s.second);
+    delete event;
+}
+int lcbEventSignal(lcbDevice *device, lcbEvent *event, lcrtStream stream, uint64_t value) {
+    LCB_DEVICE_GUARD(device);
+    if (!event) return LCRT_ERROR_INVALID_VALUE;
+    cudaEvent_t e;
+    LCB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    LCB_CUDA(cudaEventRecord(e, static_cast<cudaStream_t>(stream)));
+    std::scoped_lock lock{event->mutex};
+    // completed signals below the new value are no longer needed
+    for (auto it = event->signals.begin(); it != event->signals.end();) {
+        if (it->first < value && cudaEventQuery(it->second) == cudaSuccess) {
+            cudaEventDestroy(it->second);
+            it = event->signals.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    event->signals.emplace_back(value, e);
+    return 0;
+}
+static cudaEvent_t lcb_event_for(lcbEvent *event, uint64_t value, bool *known) {
+    std::scoped_lock lock{event->mutex};
+    cudaEvent_t best = nullptr;
+    uint64_t bv = ~0ull;
+    *known = false;
+    for (auto &s : event->signals)
+        if (s.first >= value && s.first <= bv) best = s.second, bv = s.first, *known = true;
+    return best;
+}
+int lcbEventWait(lcbDevice *device, lcbEvent *event, lcrtStream stream, uint64_t value) {
+    LCB_DEVICE_GUARD(device);
+    if (!event) return LCRT_ERROR_INVALID_VALUE;
+    bool known;
+    cudaEvent_t e = lcb_event_for(event, value, &known);
+    if (!known) return LCRT_ERROR_INVALID_VALUE;// waiting on a value nobody has signalled yet (the reference asserts this too)
+    LCB_CUDA(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), e, 0));
+    return 0;
+}
+int lcbEventSynchronize(lcbDevice *device, lcbEvent *event, uint64_t value) {
+    LCB_DEVICE_GUARD(device);
+    if (!event) return LCRT_ERROR_INVALID_VALUE;
+    bool known;
+    cudaEvent_t e = lcb_event_for(event, value, &known);
+    if (!known) return value == 0 ? 0 : LCRT_ERROR_INVALID_VALUE;
+    LCB_CUDA(cudaEventSynchronize(e));
+    return 0;
+}
+int lcbEventIsCompleted(lcbDevice *device, lcbEvent *event, uint64_t value) {
+    if (!device || !event) return 0;
+    cudaSetDevice(device->index);
+    bool known;
+    cudaEvent_t e = lcb_event_for(event, value, &known);
+    if (!known) return value == 0 ? 1 : 0;
+    return cudaEventQuery(e) == cudaSuccess ? 1 : 0;
 }
 
 }// extern "C"

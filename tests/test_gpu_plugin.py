@@ -1,0 +1,118 @@
+"""Drop-in boundary test: the `b200rt` backend plugin inside the reference's own (unmodified) host runtime.
+
+`baseline/_ref/bin/test_plugin_rtx` (plugin/test_plugin_rtx.cpp) is a C++ program written against LuisaCompute's public
+runtime API — Context / Device / Stream / Buffer / Mesh / ProceduralPrimitive / Accel — and linked against the
+reference's liblc-runtime; the Context dlopens `liblc-backend-b200rt.so` (plugin/lc_backend_b200rt.cpp), whose
+DeviceInterface forwards the accel path to liblcb200_rt.so.  The program dumps every case it ran (geometry, instances,
+rays, results); here the results are checked against the oracle on the same inputs, to the BASELINE.json bar.
+
+The binaries are built by `make -C plugin` when the reference tree and its built host libraries are present (this
+container); they travel to the GPU box under baseline/_ref/ (git-ignored, not gpurun-ignored).  Absent binaries skip.
+"""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from luisacompute_b200 import scenes as S
+
+BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "bin")
+EXE = os.path.join(BIN, "test_plugin_rtx")
+needs_plugin = pytest.mark.skipif(not os.path.exists(EXE), reason="plugin integration binaries not built (need the reference tree; make -C plugin)")
+
+INST_DTYPE = np.dtype([("blas", "<u4"), ("mask", "<u4"), ("opaque", "<u4"), ("user_id", "<u4"), ("affine", "<f4", 12)])
+
+
+def _read_cases(path):
+    raw = open(path, "rb").read()
+    pos = 0
+
+    def u32():
+        nonlocal pos
+        v = struct.unpack_from("<I", raw, pos)[0]
+        pos += 4
+        return v
+
+    def arr(dtype, count):
+        nonlocal pos
+        a = np.frombuffer(raw, dtype=dtype, count=count, offset=pos).copy()
+        pos += a.nbytes
+        return a
+
+    cases = []
+    while pos < len(raw):
+        name = raw[pos:pos + 32].split(b"\0")[0].decode()
+        pos += 32
+        meshes = []
+        for _ in range(u32()):
+            v = arr("<f4", 4 * u32()).reshape(-1, 4)
+            t = arr("<u4", 3 * u32()).reshape(-1, 3)
+            meshes.append((v, t))
+        boxes = [arr("<f4", 6 * u32()).reshape(-1, 6) for _ in range(u32())]
+        inst = arr(INST_DTYPE, u32())
+        n_rays, ray_mask = u32(), u32()
+        rays = arr(S.RAY_DTYPE, n_rays)
+        closest = arr("<u4", u32()).view(S.HIT_DTYPE)
+        anyhit = arr("<u4", u32())
+        query = arr("<u4", u32()).view(S.CHIT_DTYPE)
+        cases.append(dict(name=name, meshes=meshes, boxes=boxes, inst=inst, rays=rays, ray_mask=ray_mask, closest=closest, any=anyhit, query=query))
+    return cases
+
+
+def _oracle_scene(oracle, case):
+    geoms = [oracle.OracleMesh(v, t) for v, t in case["meshes"]]
+    procs = [oracle.OracleProcedural(b) for b in case["boxes"]]
+    acc = oracle.OracleAccel()
+    acc._keep = geoms + procs
+    inst = case["inst"]
+    handles = [(procs[b & 0x7FFFFFFF] if b & 0x80000000 else geoms[b]).handle for b in inst["blas"]]
+    mods = S.make_mods(handles, inst["affine"], inst["mask"], inst["opaque"] != 0, inst["user_id"])
+    assert acc.update(len(inst), mods) == 0
+    return acc
+
+
+@needs_plugin
+@pytest.mark.gpu
+def test_plugin_in_reference_runtime(oracle, tmp_path):
+    out = str(tmp_path / "plugin_cases.bin")
+    r = subprocess.run([EXE, out, "192"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "b200rt device:" in r.stdout + r.stderr          # backend_device_names went through the plugin
+    cases = _read_cases(out)
+    assert [c["name"] for c in cases] == ["c1_static"] + [f"c1_frame{i}" for i in range(4)] + ["c1_three_masked", "c5_procedural"]
+    for c in cases:
+        acc = _oracle_scene(oracle, c)
+        res = oracle.compare_closest(acc, c["rays"], c["closest"], int(c["ray_mask"]))
+        assert res["id_mismatch"] == 0 and res["t_bad"] == 0 and res["bary_bad"] == 0, (c["name"], res)
+        assert np.array_equal(c["any"] != 0, acc.trace_any(c["rays"], int(c["ray_mask"])) != 0), c["name"]
+        if len(c["query"]):
+            e = acc.query(c["rays"], int(c["ray_mask"]), False, 0, 0)
+            g = c["query"]
+            assert np.array_equal(e["hit_type"], g["hit_type"]), c["name"]
+            hit = e["hit_type"] != 0
+            assert np.array_equal(e["inst"][hit], g["inst"][hit]), c["name"]
+            np.testing.assert_allclose(g["t"][hit], e["t"][hit], rtol=1e-5)
+            # rays of the pixel grid that run exactly along the floor's diagonal hit both of its triangles at the same t:
+            # a different primitive id is accepted only there (BASELINE.json tie rule), never for the spheres
+            diff = hit & (e["prim"] != g["prim"])
+            assert not np.any(diff & (e["hit_type"] != 1)) and diff.sum() <= 2 * int(np.sqrt(len(g))), (c["name"], int(diff.sum()))
+            assert (e["hit_type"] == 2).sum() > 0 and (e["hit_type"] == 1).sum() > 0   # both spheres and the floor are seen
+    # the frame loop really moved things: results differ between frames
+    assert not np.array_equal(cases[1]["closest"]["t"], cases[4]["closest"]["t"])
+    # the third instance (mask 0x0f, user id 7) is visible to ray mask 0x03 and nearest where it covers the others
+    assert (cases[5]["closest"]["inst"] == 2).sum() > 0
+
+
+@needs_plugin
+def test_plugin_loads_and_fails_loudly_without_gpu():
+    """CPU side of the boundary: the reference's Context discovers and dlopens the plugin and calls `create`; without a
+    CUDA device that must be a logged error and an abort (the reference's failure mode), never a silent CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present; the loud-failure path is for GPU-less hosts")
+    r = subprocess.run([EXE, "/dev/null", "8"], capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0
+    assert "no usable CUDA device" in r.stdout + r.stderr
+    assert "liblc-backend-b200rt.so" in r.stdout + r.stderr      # the stack trace goes through the plugin's create()
