@@ -90,6 +90,9 @@ ABI_SYMBOLS = [
     "lcbAccelBuild", "lcbAccelGetBinding", "lcbLastBuildKind", "lcbNativeHandle", "lcbBlobInfo", "lcbTraceClosest", "lcbTraceAny",
     "lcbQuery", "lcbTraceClosestHost", "lcbSynchronize", "lcbDownload", "lcbUpload",
     "lcbPrimitiveExport", "lcbPrimitiveImport",
+    # plumbing used by the backend plugin (plugin/lc_backend_b200rt.cpp)
+    "lcbDeviceCount", "lcbDeviceName", "lcbBufferCreate", "lcbBufferDestroy", "lcbStreamCreate", "lcbStreamDestroy", "lcbCopyAsync",
+    "lcbHostCallback", "lcbEventCreate", "lcbEventDestroy", "lcbEventSignal", "lcbEventWait", "lcbEventSynchronize", "lcbEventIsCompleted",
 ]
 
 
