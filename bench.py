@@ -375,8 +375,17 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         achieved = bytes_b * n / (tb_ms * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload, per launch, from the committed
+        # `ncu --set full` capture (profiles/ncu_traffic.json names the report); null if the workload is not the profiled one
+        traffic = None
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_trace_closest_incoherent"]
+            if t["level"] == args.level and t["rays"] == n:
+                traffic = t["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": "k_trace<MODE_CLOSEST> on the incoherent bounce batch", "achieved": achieved, "peak": peak,
-                    "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                     "bytes_per_ray": float(bytes_b), "per_ray": {"nodes": float(cb[0]), "prims": float(cb[1]), "instances": float(cb[2])},
                     "roofline_mrays_s": peak * 1e9 / bytes_b / 1e6, "coherent": {"bytes_per_ray": float(bytes_p), "achieved": bytes_p * n / (tp_ms * 1e-3) / 1e9,
                                                                                  "per_ray": {"nodes": float(cp[0]), "prims": float(cp[1]), "instances": float(cp[2])}}}
@@ -399,7 +408,7 @@ def main():
                        "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
                        "scene_gen_s": gen_s},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 2 * K,
+            "gpu_launches": 4 * K,  # per step: k_trace + k_refine_hits for the primary batch and for the bounce batch
         }
         print(json.dumps(line))
     if world > 1:

@@ -197,12 +197,15 @@ LCRT_HD uint64_t morton63(const Box &b, const float clo[3], const float inv_ext[
     return code;
 }
 
-// Bits per axis: enough to resolve 256 cells per primitive of a uniform distribution, at most 21.  The number of
-// 8-bit radix passes follows: ceil(3 * bits / 8).
+// Bits per axis: enough to resolve 64 cells per primitive (per axis) of a uniform distribution, at most 21.  The number
+// of 8-bit radix passes follows: ceil(3 * bits / 8) — 5 passes up to 2 M primitives, 6 up to 128 M.
+#ifndef LCRT_MORTON_EXTRA_BITS
+#define LCRT_MORTON_EXTRA_BITS 6u
+#endif
 LCRT_HD uint32_t morton_bits_for(uint32_t n) {
     uint32_t lg = 0;
     while ((1ull << lg) < (uint64_t)n) lg++;
-    uint32_t b = (lg + 2u) / 3u + 8u;
+    uint32_t b = (lg + 2u) / 3u + LCRT_MORTON_EXTRA_BITS;
     if (b < 10u) b = 10u;
     if (b > 21u) b = 21u;
     return b;
