@@ -121,22 +121,250 @@ __global__ void __launch_bounds__(256) k_climb(Bvh2 t, Input in) {
 #ifndef LCRT_COLLAPSE_MIN_BLOCKS
 #define LCRT_COLLAPSE_MIN_BLOCKS 4
 #endif
-// BVH2 -> BVH8, level by level inside ONE persistent kernel: the wide nodes of a level are the contiguous index range
-// allocated while the previous level was processed, so each level is a grid-stride loop over [begin, end) followed by
-// a grid-wide barrier (arrival counter + generation word; the last block to arrive snapshots the node counter, which
-// is the next level's `end`).  The grid never exceeds what is co-resident, so the barrier can not deadlock; a level
-// costs one node latency plus ~2 us, there is no polling on individual tasks.
+constexpr int COLLAPSE_BLOCK = 128;
+#ifndef LCRT_COLLAPSE_OCTET_WAVES
+#define LCRT_COLLAPSE_OCTET_WAVES 4   // levels of up to this many grid-loads of octets use the eight-lanes-per-node path
+#endif
+
+// ---- collapse_node() (lcrt_build.h, the serial statement the host simulation runs) done by EIGHT lanes per wide node:
+// lane k of an "octet" owns child k (binary node id, box, area, leaf mark, leaf-slot count) in registers, so nothing
+// is indexed dynamically in local memory; the choices (which child to open, which (child, slot) pair to assign next)
+// are arg-max reductions over the octet with three __shfl_xor steps, and the per-child work (leaf gathering,
+// quantisation) runs in parallel.  Every decision is the serial one (same tie-breaks), so both produce the same tree.
+// All shuffles are executed by the full warp: control flow is warp-uniform, per-octet activity is a predicate.
+struct OctChild {
+    uint32_t id;
+    float lox, loy, loz, hix, hiy, hiz, area;
+    bool valid, leaf;
+    uint32_t slots, count;// leaf slots below the child; primitives in it if it is a leaf
+};
+__device__ __forceinline__ void oct_load(const Bvh2 &t, OctChild &c, uint32_t id) {
+    const f4 lo = t.lo[id], hi = t.hi[id];
+    c.id = id, c.valid = true;
+    c.lox = lo.x, c.loy = lo.y, c.loz = lo.z, c.hix = hi.x, c.hiy = hi.y, c.hiz = hi.z;
+    c.area = area_of(lo, hi);
+    c.leaf = (as_uint(hi.w) & LEAF_MARK) != 0u;
+    c.count = as_uint(hi.w) & ~LEAF_MARK;
+    c.slots = c.leaf ? 1u : (id < t.n - 1u ? t.flag[id] : 1u);
+}
+// opens child `k` of every octet with `go`: its left child stays in lane k, its right child goes to lane nc
+__device__ __forceinline__ void oct_open(const Bvh2 &t, OctChild &c, uint32_t l, bool go, uint32_t k, uint32_t &nc) {
+    u2 ch = make_u2(0u, 0u);
+    if (go && l == k) ch = t.child[c.id];
+    ch.x = __shfl_sync(0xffffffffu, ch.x, (int)k, 8), ch.y = __shfl_sync(0xffffffffu, ch.y, (int)k, 8);
+    if (go && l == k) oct_load(t, c, ch.x);
+    if (go && l == nc) oct_load(t, c, ch.y);
+    if (go) nc++;
+}
+// arg-max of `key` over the octet among lanes with `cand`; ties go to the lower lane; returns 8 if there is no candidate
+__device__ __forceinline__ uint32_t oct_argmax(float key, bool cand, uint32_t l) {
+    uint32_t who = cand ? l : 8u;
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, key, m, 8);
+        const uint32_t ow = __shfl_xor_sync(0xffffffffu, who, m, 8);
+        const bool take = ow < 8u && (who == 8u || ok > key || (ok == key && ow < who));
+        if (take) key = ok, who = ow;
+    }
+    return who;
+}
+__device__ __forceinline__ uint32_t oct_or(uint32_t v) {
+#pragma unroll
+    for (int m = 1; m < 8; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m, 8);
+    return v;
+}
+
 template<class Input>
-__global__ void __launch_bounds__(128, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *bar) {
-    const uint32_t stride = gridDim.x * blockDim.x, gtid = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid, bool act, unsigned char *node_smem) {
+    const uint32_t l = threadIdx.x & 7u;
+    OctChild c;
+    c.id = INVALID_U32, c.valid = false, c.leaf = true, c.slots = 0u, c.count = 0u, c.area = 0.f;
+    c.lox = c.loy = c.loz = INFINITY, c.hix = c.hiy = c.hiz = -INFINITY;
+    uint32_t nc = 0u;
+    if (act) {
+        const f4 hi = t.hi[bid];
+        if (as_uint(hi.w) & LEAF_MARK) {
+            nc = 1u;
+            if (l == 0u) oct_load(t, c, bid);
+        } else {
+            const u2 ch = t.child[bid];
+            nc = 2u;
+            if (l == 0u) oct_load(t, c, ch.x);
+            if (l == 1u) oct_load(t, c, ch.y);
+        }
+    }
+    // ---- open the largest child with more than 8 leaf slots until the node is full
+    for (;;) {
+        const bool cand = act && nc < 8u && c.valid && !c.leaf && c.slots > 8u;
+        const uint32_t best = oct_argmax(c.area, cand, l);
+        if (!__any_sync(0xffffffffu, best < 8u)) break;
+        oct_open(t, c, l, best < 8u, best & 7u, nc);
+    }
+    // ---- dissolve, smallest first, children whose whole subtree fits into the free slots
+    {
+        uint32_t pending = 0u;
+        bool more = act;
+        for (;;) {
+            const bool cand = more && pending == 0u && c.valid && !c.leaf && nc - 1u + c.slots <= 8u;
+            const uint32_t best = oct_argmax(-(float)c.slots, cand, l);
+            if (more && pending == 0u) {
+                if (best < 8u) pending = 1u << best;
+                else more = false;
+            }
+            if (!__any_sync(0xffffffffu, more)) break;
+            const uint32_t k = pending ? (uint32_t)bfind(pending) : 0u;
+            pending &= ~(1u << k);
+            const bool kleaf = __shfl_sync(0xffffffffu, (int)c.leaf, (int)k, 8) != 0;
+            const bool go = more && !kleaf;
+            oct_open(t, c, l, go, k, nc);
+            if (go) pending |= (1u << k) | (1u << (nc - 1u));
+        }
+    }
+    // ---- node box and centre
+    float nlx = c.lox, nly = c.loy, nlz = c.loz, nhx = c.hix, nhy = c.hiy, nhz = c.hiz;
+    if (!c.valid) nlx = nly = nlz = INFINITY, nhx = nhy = nhz = -INFINITY;
+    {
+        // box_grow semantics: NaN coordinates never enter (fminf / fmaxf return the other operand)
+#pragma unroll
+        for (int m = 1; m < 8; m <<= 1) {
+            nlx = fminf(nlx, __shfl_xor_sync(0xffffffffu, nlx, m, 8)), nly = fminf(nly, __shfl_xor_sync(0xffffffffu, nly, m, 8));
+            nlz = fminf(nlz, __shfl_xor_sync(0xffffffffu, nlz, m, 8)), nhx = fmaxf(nhx, __shfl_xor_sync(0xffffffffu, nhx, m, 8));
+            nhy = fmaxf(nhy, __shfl_xor_sync(0xffffffffu, nhy, m, 8)), nhz = fmaxf(nhz, __shfl_xor_sync(0xffffffffu, nhz, m, 8));
+        }
+    }
+    float cx = 0.5f * (nlx + nhx), cy = 0.5f * (nly + nhy), cz = 0.5f * (nlz + nhz);
+    if (!(cx == cx)) cx = 0.f;
+    if (!(cy == cy)) cy = 0.f;
+    if (!(cz == cz)) cz = 0.f;
+    // ---- octant-ordered slot assignment: nc rounds of "best (child, slot) pair among the unassigned"
+    int slot = -1;
+    {
+        float ddx = 0.5f * (c.lox + c.hix) - cx, ddy = 0.5f * (c.loy + c.hiy) - cy, ddz = 0.5f * (c.loz + c.hiz) - cz;
+        if (!(ddx == ddx)) ddx = 0.f;
+        if (!(ddy == ddy)) ddy = 0.f;
+        if (!(ddz == ddz)) ddz = 0.f;
+        uint32_t free_slots = 0xffu;
+        for (uint32_t round = 0u; round < 8u; round++) {
+            float bv = -INFINITY;
+            int bs = -1;
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                const float v = ((s & 1) ? ddx : -ddx) + ((s & 2) ? ddy : -ddy) + ((s & 4) ? ddz : -ddz);
+                if (((free_slots >> s) & 1u) && (v > bv || bs < 0)) bv = v, bs = s;
+            }
+            const bool cand = act && round < nc && c.valid && slot < 0;
+            const uint32_t who = oct_argmax(bv, cand, l);
+            const int ws = __shfl_sync(0xffffffffu, bs, (int)(who & 7u), 8);
+            if (who < 8u) {
+                if (l == who) slot = ws;
+                free_slots &= ~(1u << ws);
+            }
+        }
+    }
+    // ---- allocate internal children and primitive records
+    const bool is_int = act && c.valid && !c.leaf, is_leaf = act && c.valid && c.leaf;
+    const uint32_t int_by_slot = oct_or(is_int ? (1u << slot) : 0u);
+    const uint32_t cnt_by_slot = oct_or(is_leaf ? (c.count << (2 * slot)) : 0u);// counts <= 3: two bits per slot
+    const uint32_t n_int = (uint32_t)__popc(int_by_slot);
+    const uint32_t n_prims = (uint32_t)__popc(cnt_by_slot & 0x5555u) + 2u * (uint32_t)__popc(cnt_by_slot & 0xaaaau);
+    uint32_t child_base = 0u, prim_base = 0u;
+    if (act && l == 0u) {
+        if (n_int) child_base = atomicAdd(&o.counters[0], n_int);
+        if (n_prims) prim_base = atomicAdd(&o.counters[1], n_prims);
+    }
+    child_base = __shfl_sync(0xffffffffu, child_base, 0, 8), prim_base = __shfl_sync(0xffffffffu, prim_base, 0, 8);
+    bool ok = true;
+    if (act && n_int && child_base + n_int > o.node_capacity) {
+        if (l == 0u) o.header->error = 1u;
+        ok = false, act = false;
+    }
+    // ---- per child: schedule the internal ones, gather the leaves, quantise the box
+    Node8 *stage = reinterpret_cast<Node8 *>(node_smem) + (threadIdx.x >> 3);
+    uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
+    const bool okx = nlx <= nhx, oky = nly <= nhy, okz = nlz <= nhz;
+    const float px = okx ? nlx : 0.f, py = oky ? nly : 0.f, pz = okz ? nlz : 0.f;
+    const uint32_t ex = okx ? quant_exponent(nlx, nhx) : 0u, ey = oky ? quant_exponent(nly, nhy) : 0u, ez = okz ? quant_exponent(nlz, nhz) : 0u;
+    // defaults: empty slots have meta 0 and inverted boxes (lo 255, hi 0)
+    if (l == 0u) sw[0] = as_uint(px), sw[1] = as_uint(py), sw[2] = as_uint(pz), sw[3] = ex | (ey << 8) | (ez << 16) | (int_by_slot << 24);
+    if (l == 1u) sw[4] = child_base, sw[5] = prim_base, sw[6] = 0u, sw[7] = 0u;
+    if (l == 2u) sw[8] = sw[9] = sw[10] = sw[11] = 0xffffffffu;            // qlo_x, qlo_y
+    if (l == 3u) sw[12] = sw[13] = 0xffffffffu, sw[14] = sw[15] = 0u;       // qlo_z | qhi_x
+    if (l == 4u) sw[16] = sw[17] = sw[18] = sw[19] = 0u;                     // qhi_y, qhi_z
+    __syncwarp();
+    if (act && c.valid) {
+        uint8_t meta;
+        if (!c.leaf) {
+            const uint32_t w = child_base + (uint32_t)__popc(int_by_slot & ((1u << slot) - 1u));
+            meta = (uint8_t)((1u << 5) | (24u + (uint32_t)slot));
+            if (o.parent) o.parent[w] = (widx << 3) | (uint32_t)slot;
+            o.task[w] = c.id;
+        } else {
+            const uint32_t below = cnt_by_slot & ((1u << (2 * slot)) - 1u);
+            const uint32_t po = (uint32_t)__popc(below & 0x5555u) + 2u * (uint32_t)__popc(below & 0xaaaau);
+            uint32_t pos[4];
+            const uint32_t cnt = gather_leaf(t, c.id, pos, 3u);
+            for (uint32_t q = 0; q < cnt; q++) o.rec_src[prim_base + po + q] = pos[q];
+            const uint32_t unary = cnt == 1u ? 1u : cnt == 2u ? 3u : 7u;
+            meta = (uint8_t)((unary << 5) | po);
+        }
+        stage->meta[slot] = meta;
+        uint32_t ql, qh;
+        ql = 255u, qh = 0u;
+        if (c.lox <= c.hix) ql = quant_down(c.lox, px, ex), qh = quant_up(c.hix, px, ex);
+        stage->qlo_x[slot] = (uint8_t)ql, stage->qhi_x[slot] = (uint8_t)qh;
+        ql = 255u, qh = 0u;
+        if (c.loy <= c.hiy) ql = quant_down(c.loy, py, ey), qh = quant_up(c.hiy, py, ey);
+        stage->qlo_y[slot] = (uint8_t)ql, stage->qhi_y[slot] = (uint8_t)qh;
+        ql = 255u, qh = 0u;
+        if (c.loz <= c.hiz) ql = quant_down(c.loz, pz, ez), qh = quant_up(c.hiz, pz, ez);
+        stage->qlo_z[slot] = (uint8_t)ql, stage->qhi_z[slot] = (uint8_t)qh;
+    }
+    __syncwarp();
+    if (act && l < 5u) reinterpret_cast<uint4 *>(&o.nodes[widx])[l] = reinterpret_cast<const uint4 *>(stage)[l];
+    if (act && l == 0u) {
+        if (widx == 0u) {
+            o.header->lo[0] = nlx, o.header->lo[1] = nly, o.header->lo[2] = nlz;
+            o.header->hi[0] = nhx, o.header->hi[1] = nhy, o.header->hi[2] = nhz;
+            if (o.parent) o.parent[0] = INVALID_U32;
+        }
+        if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2], n_prims);
+    }
+    __syncwarp();
+    return ok;
+}
+
+// BVH2 -> BVH8, level by level inside ONE persistent kernel: the wide nodes of a level are the contiguous index range
+// allocated while the previous level was processed, so each level is a grid-stride loop over [begin, end) — one octet
+// of lanes per node while the level is narrow, one thread per node (collapse_node, lcrt_build.h) once it is wide; both
+// make identical decisions — followed by a grid-wide barrier (arrival counter + generation word; the last block to arrive
+// snapshots the node counter, which is the next level's `end`).  The grid never exceeds what is co-resident, so the
+// barrier can not deadlock; there is no polling on individual tasks.
+template<class Input>
+__global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *bar) {
+    __shared__ __align__(16) unsigned char node_smem[(COLLAPSE_BLOCK / 8) * sizeof(Node8)];
+    const uint32_t octets = COLLAPSE_BLOCK / 8u;
+    const uint32_t stride = gridDim.x * octets, goct = blockIdx.x * octets + (threadIdx.x >> 3);
     __shared__ uint32_t s_end;
     uint32_t begin = 0u, end = 1u, gen = 0u;
     while (begin < end) {
-        for (uint32_t w = begin + gtid; w < end; w += stride) {
-            const uint32_t bid = (w == 0u) ? *t.root : LCRT_VOLATILE_LOAD_U32(&o.task[w]);
-            if (bid == INVALID_U32 || !collapse_node(t, o, in, w, bid)) atomicExch(abort_flag, 1u);
+        if (end - begin <= stride * (uint32_t)LCRT_COLLAPSE_OCTET_WAVES) {
+            // narrow level: latency matters (the top of the tree is a chain of such levels) -> eight lanes per node
+            for (uint32_t base = begin; base < end; base += stride) {// warp-uniform trip count
+                const uint32_t w = base + goct;
+                bool act = w < end;
+                uint32_t bid = INVALID_U32;
+                if (act) bid = (w == 0u) ? *t.root : LCRT_VOLATILE_LOAD_U32(&o.task[w]);
+                if (act && bid == INVALID_U32) atomicExch(abort_flag, 1u), act = false;
+                if (!collapse_octet(t, o, in, w, bid, act, node_smem)) atomicExch(abort_flag, 1u);
+            }
+        } else {
+            // wide level: throughput matters -> one thread per node (eight times as many nodes in flight)
+            for (uint32_t w = begin + blockIdx.x * blockDim.x + threadIdx.x; w < end; w += gridDim.x * blockDim.x) {
+                const uint32_t bid = LCRT_VOLATILE_LOAD_U32(&o.task[w]);
+                if (bid == INVALID_U32 || !collapse_node(t, o, in, w, bid)) atomicExch(abort_flag, 1u);
+            }
         }
-        // ---- grid barrier
+        // ---- grid barrier (tasks and parents written above are released by the fence before the arrival)
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -537,17 +765,17 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     {
         int &bps = dev->collapse_blocks_per_sm[Input::kind];
         if (bps == 0) {
-            LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_collapse<Input>, 128, 0));
+            LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_collapse<Input>, COLLAPSE_BLOCK, 0));
             if (bps < 1) bps = 1;
         }
         uint32_t g = (uint32_t)(dev->sm_count * bps);
-        const uint32_t need = (L.node_capacity + 127u) / 128u;
+        const uint32_t need = (L.node_capacity + COLLAPSE_BLOCK / 8u - 1u) / (COLLAPSE_BLOCK / 8u);
         if (g > need) g = need;
         // cooperative launch: the runtime guarantees that all blocks are co-resident (the kernel has a grid barrier)
         uint32_t *abort_flag = small + SM_ABORT, *bar = small + SM_BARRIER;
         Input in_arg = in;
         void *args[] = {&t, &o, &in_arg, &abort_flag, &bar};
-        LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(128), args, 0, stream));
+        LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(COLLAPSE_BLOCK), args, 0, stream));
     }
     k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in);
     LCRT_LAUNCH_CHECK("k_emit_records");
