@@ -212,6 +212,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA GPU: luisacompute_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = None
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        from luisacompute_b200.dist import bind_to_gpu_numa
+        numa = bind_to_gpu_numa(local_rank)   # pinned host buffers of the e2e path next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = lc.Device(local_rank)
@@ -405,7 +409,7 @@ def main():
             "detail": {"coherent_closest_mrays_s": world * n / (tp_ms * 1e-3) / 1e6, "incoherent_closest_mrays_s": world * n / (tb_ms * 1e-3) / 1e6,
                        "incoherent_any_mrays_s": n / (any_ms * 1e-3) / 1e6, "primary_hit_fraction": hit_frac_p,
                        "blas_build_ms": build_ms, "blas_build_mtris_s": (ntris / (build_ms * 1e-3) / 1e6) if build_ms else None,
-                       "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
+                       "numa_binding": list(numa) if numa else None, "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
                        "scene_gen_s": gen_s},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": 4 * K,  # per step: k_trace + k_refine_hits for the primary batch and for the bounce batch
