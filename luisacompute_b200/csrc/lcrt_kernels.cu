@@ -473,9 +473,6 @@ constexpr uint32_t TRACE_BATCH = 128; // rays a warp reserves per atomic
 #ifndef LCRT_TRI_VOTE
 #define LCRT_TRI_VOTE 4               // lanes with a pending primitive that make the warp run the primitive phase
 #endif
-#ifndef LCRT_DEFER_PRIMS
-#define LCRT_DEFER_PRIMS 0            // park hit leaf slots and go on with nodes (Traversal::DEFER)
-#endif
 #ifndef LCRT_STREAM_HITS
 #define LCRT_STREAM_HITS 1
 #endif
@@ -501,7 +498,6 @@ __device__ __forceinline__ TraceSmem *trace_smem() {
 }
 struct HybridStore {
     static constexpr bool world_in_global = true;
-    static constexpr bool defer_prims = LCRT_DEFER_PRIMS != 0;
     u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
     __device__ __forceinline__ void store(int i, u2 v) {
         if (i < TRACE_SMEM_STACK) trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] = v;
@@ -612,10 +608,10 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
             // lanes with a pending primitive wait until LCRT_TRI_VOTE of them (or every live lane) can go together
             const uint32_t am = __ballot_sync(0xffffffffu, alive);
             const uint32_t pm = __ballot_sync(0xffffffffu, alive && tr.prim_pending());
-            if ((uint32_t)__popc(pm) >= (uint32_t)LCRT_TRI_VOTE || pm == am) alive = alive && tr.step_prim(true);
+            if ((uint32_t)__popc(pm) >= (uint32_t)LCRT_TRI_VOTE || pm == am) alive = alive && tr.step_prim();
         }
 #else
-        alive = alive && tr.step_prim(false);
+        alive = alive && tr.step_prim();
 #endif
         if (active && !alive) active = false, unsaved = true;
     }

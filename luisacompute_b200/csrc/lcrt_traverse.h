@@ -73,13 +73,10 @@ enum ColdWord : int {
     CW_HIT_TD_LO, // exact t of the best hit as a double, valid iff CW_HIT_EXACT
     CW_HIT_TD_HI,
     CW_HIT_EXACT,
-    CW_DEF_X,     // deferred primitive group (Store::defer_prims): node index, hit leaf slots
-    CW_DEF_Y,
     CW_COUNT
 };
 struct LocalStore {
     static constexpr bool world_in_global = false;
-    static constexpr bool defer_prims = false;
     u2 e[LCRT_STACK_SIZE];
     f4 rows[2];
     uint32_t words[CW_COUNT];
@@ -89,10 +86,6 @@ struct LocalStore {
     LCRT_HD f4 ld4(int k) const { return rows[k]; }
     LCRT_HD void stw(int k, uint32_t v) { words[k] = v; }
     LCRT_HD uint32_t ldw(int k) const { return words[k]; }
-};
-// same storage with primitive deferral on (exercises the batch kernel's schedule in the host simulation)
-struct LocalStoreDefer : LocalStore {
-    static constexpr bool defer_prims = true;
 };
 
 LCRT_HD float safe_dir(float d) {
@@ -121,27 +114,7 @@ LCRT_HD T ldg16(const T *p) {
 #endif
 }
 
-// BVH loads that ask L2 to keep the line (evict_last policy), and ray loads that ask it not to: the rays and hit
-// records of a batch stream through L2 once and would otherwise push node / triangle lines out
-#if defined(__CUDA_ARCH__) && defined(LCRT_L2_HINTS)
-__device__ __forceinline__ uint64_t l2_keep_policy() {
-    uint64_t pol;
-    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-template<class T>
-__device__ __forceinline__ T ldg16_keep(const T *p, uint64_t pol) {
-    uint32_t x, y, z, w;
-    asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(x), "=r"(y), "=r"(z), "=r"(w) : "l"(p), "l"(pol));
-    T r;
-    uint32_t *q = reinterpret_cast<uint32_t *>(&r);
-    q[0] = x, q[1] = y, q[2] = z, q[3] = w;
-    return r;
-}
-#define LCRT_LDK(p) ldg16_keep(p, l2keep)
-#else
-#define LCRT_LDK(p) ldg16(p)
-#endif
+// rays are read exactly once per batch: streaming loads keep them from pushing node / triangle lines out of L2
 template<class T>
 LCRT_HD T ld16_stream(const T *p) {
 #if defined(__CUDA_ARCH__) && !defined(LCRT_NO_STREAM_RAYS)
@@ -394,7 +367,6 @@ struct Traversal {
     int sp, blas_sp;   // blas_sp < 0: traversing the TLAS
     uint32_t cur_inst, cur_flags, ray_mask;
     bool done;
-    bool defd;         // a deferred primitive group is parked in CW_DEF_X / CW_DEF_Y (BLAS level only)
     // ---- level-independent
     const Ray *world;  // the ray as given (re-read on instance exit, by the fallback and by the RayQuery callbacks)
     const u4 *tlas_nodes;
@@ -404,9 +376,6 @@ struct Traversal {
     Callbacks *cb;
     TraceCounters ctr;
     bool terminate_on_first = false;// query_any
-#if defined(__CUDA_ARCH__) && defined(LCRT_L2_HINTS)
-    uint64_t l2keep = l2_keep_policy();
-#endif
     uint32_t magic = PLANT_MAGIC;   // see plant_byte(); the batch kernel overwrites it with the same value from a kernel parameter
     static constexpr uint32_t RAY_PENDING = 0xffffffffu;// octinv value: the current-space ray must be (re)derived
     LCRT_HD bool MODE_ANY_QUERY() const { return MODE == MODE_QUERY && terminate_on_first; }
@@ -463,7 +432,6 @@ struct Traversal {
         Gt = single ? make_u2(0u, 1u << 8) : make_u2(0u, 0u);
         tp = 0u;
         sp = 0, blas_sp = -1;
-        defd = false;
         cur_inst = ~0u, cur_flags = 0u;
         store->stw(CW_HIT_T, as_uint(tmax_)), store->stw(CW_HIT_TERR, as_uint(-1.0f));
         store->stw(CW_HIT_INST, ~0u), store->stw(CW_HIT_PRIM, ~0u), store->stw(CW_HIT_TYPE, HIT_MISS);
@@ -594,7 +562,7 @@ struct Traversal {
     // one candidate triangle; returns true if the traversal terminates
     LCRT_HD bool test_triangle(uint32_t pi) {
         const f4 *tr = reinterpret_cast<const f4 *>(prims + (uint64_t)pi * sizeof(TriRecord));
-        const f4 v0 = LCRT_LDK(tr), v1 = LCRT_LDK(tr + 1), v2 = LCRT_LDK(tr + 2);
+        const f4 v0 = ldg16(tr), v1 = ldg16(tr + 1), v2 = ldg16(tr + 2);
         float t, terr;
         const int verdict = tri_test_f32(ox, oy, oz, store->ld4(0), store->ld4(1), as_float(store->ldw(CW_SZ)), store->ldw(CW_KZ), v0, v1, v2, t, terr);
         if (verdict == TRI_MISS) return false;
@@ -636,28 +604,13 @@ struct Traversal {
 
     // step() = step_node() followed by step_prim(); the batch kernel calls the halves separately so that the warp can
     // vote on when the (poorly converged) primitive phase is worth running.  Both return true while there is more work.
-    //
-    // Primitive deferral (Store::defer_prims, BLAS level): the leaf slots a node test hits are parked instead of
-    // being tested at once, and the lane goes on with nodes; the parked group becomes the current one (Gt, which
-    // blocks node work until drained) when the next group arrives, when the instance or the ray is about to end, or
-    // when step_prim(true) is called because enough other lanes want the primitive phase anyway.  Tests are only
-    // delayed by a node or two, so little culling is lost, and the primitive phase runs far less often per warp.
-    static constexpr bool DEFER = Store::defer_prims;
     LCRT_HD bool prim_pending() const { return Gt.y != 0u; }
-    LCRT_HD bool step() { return step_node() && step_prim(false); }
-    LCRT_HD void unpark() {
-        Gt = make_u2(store->ldw(CW_DEF_X), store->ldw(CW_DEF_Y));
-        defd = false;
-    }
+    LCRT_HD bool step() { return step_node() && step_prim(); }
 
     LCRT_HD bool step_node() {
         if (done) return false;
         // ---- pop when both groups are exhausted
         if ((G.y & 0xff000000u) == 0u && Gt.y == 0u) {
-            if (DEFER && defd && (sp == 0 || sp == blas_sp)) {
-                unpark();// last call before this level is left
-                return true;
-            }
             if (blas_sp >= 0 && sp == blas_sp) leave_instance();
             if (sp == 0) {
                 done = true;
@@ -679,44 +632,25 @@ struct Traversal {
             const uint32_t rel = (uint32_t)popc(imask_parent & ~(0xffffffffu << slot));
             const uint32_t ni = base + rel;
             const u4 *n = nodes + (uint64_t)ni * 5u;
-            const u4 n0 = LCRT_LDK(n), n2 = LCRT_LDK(n + 2), n3 = LCRT_LDK(n + 3), n4 = LCRT_LDK(n + 4);
-            const uint32_t child_base = LCRT_LDK(n + 1).x;
+            const u4 n0 = ldg16(n), n2 = ldg16(n + 2), n3 = ldg16(n + 3), n4 = ldg16(n + 4);
+            const uint32_t child_base = ldg16(n + 1).x;
             if (COUNT) ctr.nodes++;
             const uint32_t hm = intersect_node8(n0, n2, n3, n4, ox, oy, oz, idx, idy, idz, tmin, tmax, magic);
             const uint32_t imask = n0.w >> 24;
             G = make_u2(child_base, (permute_slots(hm & imask, octinv) << 24) | imask);
-            const uint32_t leaf_hits = hm & ~imask;
-            if (!DEFER || blas_sp < 0) {
-                Gt = make_u2(ni, leaf_hits);
-            } else if (leaf_hits != 0u) {
-                if (defd) Gt = make_u2(store->ldw(CW_DEF_X), store->ldw(CW_DEF_Y));
-                store->stw(CW_DEF_X, ni), store->stw(CW_DEF_Y, leaf_hits);
-                defd = true;
-            }
-#if defined(__CUDA_ARCH__) && defined(LCRT_PREFETCH_NODE)
-            // the node this lane visits next (first hit child) is known now but only loaded after the primitive phase
-            // and the refill vote: ask for its lines early
-            if (G.y & 0xff000000u) {
-                const uint32_t s2 = (uint32_t)(bfind(G.y) - 24) ^ octinv;
-                const char *nx = reinterpret_cast<const char *>(nodes + (uint64_t)(child_base + (uint32_t)popc(imask & ~(0xffffffffu << s2))) * 5u);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 64));
-            }
-#endif
+            Gt = make_u2(ni, hm & ~imask);
         }
         return true;
     }
 
-    // `join`: take the parked group along even though nothing forces it yet
-    LCRT_HD bool step_prim(bool join) {
-        if (DEFER && join && defd && Gt.y == 0u) unpark();
+    LCRT_HD bool step_prim() {
         // ---- one primitive
         if (Gt.y != 0u) {
             if ((Gt.y >> 8) == 0u) {
                 // open the next hit leaf slot: its records are prim_base + offset .. + count
                 const uint32_t s = (uint32_t)bfind(Gt.y);
                 Gt.y &= ~(1u << s);
-                const u4 n1 = LCRT_LDK(nodes + (uint64_t)Gt.x * 5u + 1);
+                const u4 n1 = ldg16(nodes + (uint64_t)Gt.x * 5u + 1);
                 const uint32_t meta = (((s & 4u) ? n1.w : n1.z) >> (8u * (s & 3u))) & 0xffu;
                 const uint32_t unary = meta >> 5;// 0 (empty slot), 1, 3 or 7
                 tp = n1.y + (meta & 31u);

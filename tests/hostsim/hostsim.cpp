@@ -240,21 +240,20 @@ int hs_validate(const void *blob_, uint64_t *stats) {
 }
 
 // ---- tracing with the device traversal code -----------------------------------------------------------------
-// schedule of the two step halves: 0 = step() as the inline entry points do, 1 = primitive deferral with the
-// `join` argument toggled pseudo-randomly (what a warp vote looks like from one lane)
-static int g_defer = 0;
-void hs_set_defer(int on) { g_defer = on; }
+// schedule of the two step halves: 0 = step() as the inline entry points do, 1 = the batch kernel's: step_prim() only
+// runs when the warp votes for it, which from one lane's point of view is a pseudo-random delay of its primitive tests
+static int g_voted = 0;
+void hs_set_defer(int on) { g_voted = on; }
 extern "C++" template<class Tr>
 void run_ray(Tr &tr, uint64_t i) {
-    if (!Tr::DEFER) {
+    if (!g_voted) {
         while (tr.step()) {}
         return;
     }
     uint32_t lcg = (uint32_t)i * 2654435761u + 12345u;
     while (tr.step_node()) {
         lcg = lcg * 1664525u + 1013904223u;
-        const bool vote = (lcg >> 29) < 3u;
-        if ((tr.prim_pending() || vote) && !tr.step_prim(vote)) break;
+        if ((lcg >> 29) < 3u && !tr.step_prim()) break;
     }
 }
 
@@ -282,8 +281,7 @@ void trace_closest_impl(const void *tlas, const void *instances, const void *ray
 }
 void hs_trace_closest(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
                       void *hits_, uint64_t *counters) {
-    if (g_defer) trace_closest_impl<LocalStoreDefer>(tlas, instances, rays_, n, masks, mask_stride, hits_, counters);
-    else trace_closest_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, hits_, counters);
+    trace_closest_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, hits_, counters);
 }
 
 extern "C++" template<class St>
@@ -299,8 +297,7 @@ void trace_any_impl(const void *tlas, const void *instances, const void *rays_, 
     }
 }
 void hs_trace_any(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride, uint32_t *out) {
-    if (g_defer) trace_any_impl<LocalStoreDefer>(tlas, instances, rays_, n, masks, mask_stride, out);
-    else trace_any_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, out);
+    trace_any_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, out);
 }
 
 extern "C++" template<class St>
@@ -323,8 +320,7 @@ void query_impl(const void *tlas, const void *instances, const void *rays_, uint
 }
 void hs_query(const void *tlas, const void *instances, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
               int terminate_on_first, uint32_t tri_prog, uint32_t proc_prog, void *hits_) {
-    if (g_defer) query_impl<LocalStoreDefer>(tlas, instances, rays_, n, masks, mask_stride, terminate_on_first, tri_prog, proc_prog, hits_);
-    else query_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, terminate_on_first, tri_prog, proc_prog, hits_);
+    query_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, terminate_on_first, tri_prog, proc_prog, hits_);
 }
 
 }// extern "C"
