@@ -82,13 +82,22 @@ __global__ void __launch_bounds__(256) k_centroid_bounds(Input in, uint32_t *sma
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
     }
-    if ((threadIdx.x & 31u) == 0u) {
+    // one set of atomics per block (the six words are a hot spot: per-warp atomics cost a third of this kernel's time)
+    __shared__ float s_lo[3][8], s_hi[3][8];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    if (lane == 0u) {
 #pragma unroll
-        for (int a = 0; a < 3; a++) {
-            if (lo[a] <= hi[a]) {
-                atomicMin(&small[SM_CMIN + a], float_to_ordered(lo[a]));
-                atomicMax(&small[SM_CMAX + a], float_to_ordered(hi[a]));
-            }
+        for (int a = 0; a < 3; a++) s_lo[a][warp] = lo[a], s_hi[a][warp] = hi[a];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3u) {
+        const int a = (int)threadIdx.x;
+        float l = INFINITY, h = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < 8; w++) l = fminf(l, s_lo[a][w]), h = fmaxf(h, s_hi[a][w]);
+        if (l <= h) {
+            atomicMin(&small[SM_CMIN + a], float_to_ordered(l));
+            atomicMax(&small[SM_CMAX + a], float_to_ordered(h));
         }
     }
 }

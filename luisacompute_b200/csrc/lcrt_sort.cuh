@@ -2,8 +2,8 @@
 //
 // Per pass: (1) k_sort_hist: per-tile digit histogram, written digit-major so that ONE exclusive scan over the
 // flattened [digit][tile] table yields every tile's global scatter base; (2) a three-kernel exclusive scan;
-// (3) k_sort_scatter: stable scatter — each warp ranks 32 consecutive keys per round with __match_any_sync, warp
-// totals are combined across the tile's eight warps in shared memory.
+// (3) k_sort_scatter: stable scatter — each warp ranks 32 consecutive keys per round (same-digit peers from eight
+// ballots), warp totals are combined across the tile's eight warps in shared memory.
 //
 // HBM traffic per pass and key: 8 B (hist read) + 12 B (read) + 12 B (write); the table is n/4096 * 1 KiB.
 // The reference has no sort of its own (its optional `lcub` extension wraps cub::DeviceRadixSort,
@@ -137,8 +137,15 @@ __global__ void __launch_bounds__(SORT_THREADS)
     for (int r = 0; r < SORT_ITEMS; r++) {
         const uint32_t i = base + r * 32 + lane;
         const bool valid = i < n;
-        const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & 255u) : (256u + lane);// invalid lanes match nobody
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t d = valid ? ((uint32_t)(key[r] >> shift) & 255u) : 0u;
+        // lanes holding the same digit: eight ballots (one per digit bit) — constant cost, where MATCH.ANY takes one
+        // round per distinct value in the warp (up to 32 once the keys are shuffled by the earlier passes)
+        uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+        for (int b = 0; b < 8; b++) {
+            const uint32_t m = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+            peers &= ((d >> b) & 1u) ? m : ~m;
+        }
         uint32_t prev = 0u;
         if (valid) prev = warp_cnt[warp][d];
         __syncwarp();
