@@ -155,6 +155,27 @@ def lib():
     L.lcbPrimitiveExport.argtypes = [vp, vp, u64, vp, u64, C.POINTER(u64)]
     L.lcbPrimitiveImport.argtypes = [vp, vp, u64, vp, u64]
     L.lcbUpload.argtypes = [vp, vp, u64, vp, u64]
+    # plumbing of the backend plugin (buffers, streams, copies, host callbacks, timeline events)
+    L.lcbDeviceCount.restype = i32
+    L.lcbDeviceName.argtypes = [i32, C.c_char_p, i32]
+    L.lcbBufferCreate.restype = u64
+    L.lcbBufferCreate.argtypes = [vp, u64]
+    L.lcbBufferDestroy.restype = None
+    L.lcbBufferDestroy.argtypes = [vp, u64]
+    L.lcbStreamCreate.restype = vp
+    L.lcbStreamCreate.argtypes = [vp]
+    L.lcbStreamDestroy.restype = None
+    L.lcbStreamDestroy.argtypes = [vp, vp]
+    L.lcbCopyAsync.argtypes = [vp, vp, vp, vp, u64]
+    L.lcbHostCallback.argtypes = [vp, vp, vp, vp]
+    L.lcbEventCreate.restype = vp
+    L.lcbEventCreate.argtypes = [vp]
+    L.lcbEventDestroy.restype = None
+    L.lcbEventDestroy.argtypes = [vp, vp]
+    L.lcbEventSignal.argtypes = [vp, vp, vp, u64]
+    L.lcbEventWait.argtypes = [vp, vp, vp, u64]
+    L.lcbEventSynchronize.argtypes = [vp, vp, u64]
+    L.lcbEventIsCompleted.argtypes = [vp, vp, u64]
     _LIB = L
     return L
 

@@ -116,3 +116,46 @@ def test_plugin_loads_and_fails_loudly_without_gpu():
     assert r.returncode != 0
     assert "no usable CUDA device" in r.stdout + r.stderr
     assert "liblc-backend-b200rt.so" in r.stdout + r.stderr      # the stack trace goes through the plugin's create()
+
+
+@pytest.mark.gpu
+def test_plugin_plumbing_entry_points():
+    """The C API the plugin builds DeviceInterface's buffer / stream / event methods from, driven directly: copies are
+    stream ordered, host callbacks run after the work queued before them, events are timeline fences."""
+    import ctypes as C
+
+    import luisacompute_b200 as lc
+    L = lc.lib()
+    assert L.lcbDeviceCount() >= 1
+    name = C.create_string_buffer(256)
+    assert L.lcbDeviceName(0, name, 256) == 0 and len(name.value) > 0
+    dev = lc.Device(0)
+    h = dev._h
+    n = 1 << 22
+    src = np.arange(n, dtype=np.uint32)
+    dst = np.zeros(n, dtype=np.uint32)
+    a, b = L.lcbBufferCreate(h, src.nbytes), L.lcbBufferCreate(h, src.nbytes)
+    assert a not in (0, 0xFFFFFFFFFFFFFFFF) and b not in (0, 0xFFFFFFFFFFFFFFFF)
+    s0, s1 = L.lcbStreamCreate(h), L.lcbStreamCreate(h)
+    assert s0 and s1
+    ev = L.lcbEventCreate(h)
+    assert L.lcbEventIsCompleted(h, ev, 0) == 1 and L.lcbEventIsCompleted(h, ev, 1) == 0
+    order = []
+    CB = C.CFUNCTYPE(None, C.c_void_p)
+    cb = CB(lambda _: order.append(int(dst[-1])))
+    # stream 0: upload, device-to-device copy, signal 1; stream 1: wait 1, download, callback (sees the data), signal 2
+    assert L.lcbCopyAsync(h, s0, a, src.ctypes.data, src.nbytes) == 0
+    assert L.lcbCopyAsync(h, s0, b, a, src.nbytes) == 0
+    assert L.lcbEventSignal(h, ev, s0, 1) == 0
+    assert L.lcbEventWait(h, ev, s1, 1) == 0
+    assert L.lcbCopyAsync(h, s1, dst.ctypes.data, b, src.nbytes) == 0
+    assert L.lcbHostCallback(h, s1, C.cast(cb, C.c_void_p), None) == 0
+    assert L.lcbEventSignal(h, ev, s1, 2) == 0
+    assert L.lcbEventWait(h, ev, s0, 5) != 0            # nobody has signalled 5: an error, not a hang
+    assert L.lcbEventSynchronize(h, ev, 2) == 0
+    assert L.lcbEventIsCompleted(h, ev, 2) == 1 and L.lcbEventIsCompleted(h, ev, 1) == 1
+    assert order == [n - 1] and np.array_equal(dst, src)
+    L.lcbEventDestroy(h, ev)
+    L.lcbStreamDestroy(h, s0), L.lcbStreamDestroy(h, s1)
+    L.lcbBufferDestroy(h, a), L.lcbBufferDestroy(h, b)
+    dev.close()
