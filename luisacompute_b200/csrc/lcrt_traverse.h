@@ -396,7 +396,9 @@ struct Traversal {
         idx = rcp_fast(sdx), idy = rcp_fast(sdy), idz = rcp_fast(sdz);
         const uint32_t oct = (sdx < 0.f ? 1u : 0u) | (sdy < 0.f ? 2u : 0u) | (sdz < 0.f ? 4u : 0u);
         octinv = 7u - oct;
-        // shear rows for the triangle test: kz = dominant axis, (kx, ky, kz) cyclic.  Branch-free on purpose.
+        // shear rows for the triangle test (only primitives are tested with them, and those hang below BLAS nodes: a ray
+        // that returns to the TLAS skips this part): kz = dominant axis, (kx, ky, kz) cyclic.  Branch-free on purpose.
+        if (blas_sp < 0) return;
         const float adx = fabsf(dx), ady = fabsf(dy), adz = fabsf(dz);
         const bool k0 = adx >= ady && adx >= adz, k1 = !k0 && ady >= adz, k2 = !k0 && !k1;
         const float dk = k0 ? dx : k1 ? dy : dz;
