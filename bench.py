@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=1048576, help="rays per batch for the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the run of the reference's own CUDA/OptiX backend")
     return ap.parse_args()
 
 
@@ -149,6 +150,46 @@ def cpu_baseline(verts, tris, primary, bounce, sample: int, threads: int = 0) ->
             "note": "scalar double-precision CPU restatement of the Embree-backed reference path; real Embree (AVX-512 BVH8) would be several x faster"}
 
 
+def reference_gpu(verts, tris, primary, bounce) -> dict:
+    """The REFERENCE's own GPU path on the same scene and rays, in the same run: LuisaCompute's `cuda` backend (OptiX,
+    which is driver software traversal on B200) through baseline/_ref/bin/ref_optix_bench (baseline/ref_optix_bench.cpp: a
+    DSL kernel calling accel.intersect over the ray buffer; unmodified reference sources, see
+    baseline/build_reference_cuda_backend.sh).  Separate process, nothing of this repository loaded into it.  Returns
+    {"unavailable": why} when the binaries did not travel with the tree or the backend does not start on this box."""
+    import shutil
+    import subprocess
+    import tempfile
+    bindir = os.path.join(ROOT, "baseline", "_ref", "bin")
+    exe = os.path.join(bindir, "ref_optix_bench")
+    if not (os.path.exists(exe) and os.path.exists(os.path.join(bindir, "liblc-backend-cuda.so"))):
+        return {"unavailable": "baseline/_ref/bin/ref_optix_bench or liblc-backend-cuda.so not present"}
+    d = tempfile.mkdtemp(prefix="lc_ref_")
+    try:
+        v4 = np.zeros((len(verts), 4), dtype=np.float32)
+        v4[:, :3] = np.asarray(verts, dtype=np.float32)[:, :3]
+        v4.tofile(os.path.join(d, "verts.bin"))
+        np.ascontiguousarray(tris, dtype=np.uint32).tofile(os.path.join(d, "tris.bin"))
+        primary.tofile(os.path.join(d, "rays_primary.bin"))
+        bounce.tofile(os.path.join(d, "rays_bounce.bin"))
+        env = dict(os.environ, LD_LIBRARY_PATH=bindir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        r = subprocess.run([exe, d], capture_output=True, text=True, timeout=600, env=env)
+        path = os.path.join(d, "ref_result.json")
+        if r.returncode != 0 or not os.path.exists(path):
+            return {"unavailable": f"reference program failed (rc {r.returncode}): " + (r.stdout + r.stderr)[-300:].replace("\n", " ")}
+        res = json.load(open(path))
+        n = res["primary"]["rays"] + res["bounce"]["rays"]
+        ms = res["primary"]["closest_ms"] + res["bounce"]["closest_ms"]
+        return {"what": "LuisaCompute cuda backend (OptiX) on this GPU, same scene and rays, DSL kernel accel.intersect per ray; best of 10, host clock "
+                        "around dispatch + synchronize", "value": n / ms / 1e3, "unit": "Mrays/s",
+                "coherent_closest_mrays_s": res["primary"]["closest_mrays_s"], "incoherent_closest_mrays_s": res["bounce"]["closest_mrays_s"],
+                "incoherent_any_mrays_s": res["bounce"]["any_mrays_s"], "mesh_build_ms": res["mesh_build_ms"],
+                "mesh_build_mtris_s": res["triangles"] / res["mesh_build_ms"] / 1e3}
+    except Exception as e:  # noqa: BLE001 - a measurement aid must never take the bench line down
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU path (oracle port; Embree itself is not buildable here) on host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -192,6 +233,9 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    # for information: the reference's own GPU path (CUDA backend / OptiX) on the same sampled rays, if its binaries are here
+    if not args.no_reference_gpu:
+        line["reference_gpu"] = reference_gpu(verts, tris, ps, bs)
     print(json.dumps(line))
 
 
@@ -396,6 +440,7 @@ def main():
         cpu = None
         if not args.no_cpu_baseline:
             cpu = cpu_baseline(verts, tris, primary, bounce, args.cpu_sample)
+        ref_gpu = reference_gpu(verts, tris, primary, bounce) if (world == 1 and not args.no_reference_gpu) else None
         hit_frac_p = float(np.mean(hp["inst"] != 0xFFFFFFFF))
         line = {
             "metric": "closest-hit ray throughput (coherent primary + incoherent bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -411,7 +456,7 @@ def main():
                        "blas_build_ms": build_ms, "blas_build_mtris_s": (ntris / (build_ms * 1e-3) / 1e6) if build_ms else None,
                        "numa_binding": list(numa) if numa else None, "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
                        "scene_gen_s": gen_s},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "clocks": clocks,
             "gpu_launches": 4 * K,  # per step: k_trace + k_refine_hits for the primary batch and for the bounce batch
         }
         print(json.dumps(line))
