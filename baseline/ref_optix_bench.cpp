@@ -112,6 +112,12 @@ static int run_scene(const std::string &dir, uint32_t ray_mask, Device &device, 
     for (auto &m : meshes) stream << m.build();
     if (n_procs == 1u) stream << spheres.build();
     stream << accel.build() << synchronize();
+    double tlas_ms = 1e30;
+    for (int i = 0; i < 5; i++) {
+        Clock clk;
+        stream << accel.build(AccelBuildRequest::FORCE_BUILD) << synchronize();
+        tlas_ms = std::min(tlas_ms, clk.toc());
+    }
 
     Kernel1D closest_kernel = [](BufferVar<Ray> rays, BufferVar<TriangleHit> hits, AccelVar accel, UInt mask) noexcept {
         auto i = dispatch_id().x;
@@ -185,7 +191,7 @@ static int run_scene(const std::string &dir, uint32_t ray_mask, Device &device, 
     write_file(dir + "/ref_scene_any.bin", occ.data(), n * sizeof(uint));
     write_file(dir + "/ref_scene_query.bin", qhits.data(), n * sizeof(CommittedHit));
     std::string json = "{\"backend\": \"cuda (OptiX)\", \"instances\": " + std::to_string(n_inst) + ", \"rays\": " + std::to_string(n) +
-                       ", \"closest_ms\": " + std::to_string(closest_ms) + ", \"closest_mrays_s\": " + std::to_string((double)n / closest_ms / 1e3) + "}";
+                       ", \"tlas_build_ms\": " + std::to_string(tlas_ms) + ", \"closest_ms\": " + std::to_string(closest_ms) + ", \"closest_mrays_s\": " + std::to_string((double)n / closest_ms / 1e3) + "}";
     write_file(dir + "/ref_scene_result.json", json.data(), json.size());
     printf("%s\n", json.c_str());
     return 0;
