@@ -57,6 +57,12 @@ static void write_file(const std::string &path, const void *p, size_t bytes) {
     fclose(f);
 }
 
+// "cuda" = the reference's OptiX backend; LC_BACKEND=b200 selects the hybrid (same backend, this repository's BVH and traversal)
+static const char *backend_name() noexcept {
+    auto e = getenv("LC_BACKEND");
+    return e != nullptr ? e : "cuda";
+}
+
 struct InstanceDesc {
     uint32_t blas, mask, opaque, user_id;
     float affine[12];
@@ -190,7 +196,7 @@ static int run_scene(const std::string &dir, uint32_t ray_mask, Device &device, 
     write_file(dir + "/ref_scene_hits.bin", hits.data(), n * sizeof(TriangleHit));
     write_file(dir + "/ref_scene_any.bin", occ.data(), n * sizeof(uint));
     write_file(dir + "/ref_scene_query.bin", qhits.data(), n * sizeof(CommittedHit));
-    std::string json = "{\"backend\": \"cuda (OptiX)\", \"instances\": " + std::to_string(n_inst) + ", \"rays\": " + std::to_string(n) +
+    std::string json = "{\"backend\": \"" + std::string{backend_name()} + "\", \"instances\": " + std::to_string(n_inst) + ", \"rays\": " + std::to_string(n) +
                        ", \"tlas_build_ms\": " + std::to_string(tlas_ms) + ", \"closest_ms\": " + std::to_string(closest_ms) + ", \"closest_mrays_s\": " + std::to_string((double)n / closest_ms / 1e3) + "}";
     write_file(dir + "/ref_scene_result.json", json.data(), json.size());
     printf("%s\n", json.c_str());
@@ -201,7 +207,7 @@ int main(int argc, char *argv[]) {
     log_level_info();
     if (argc >= 3 && std::string{argv[2]} == "scene") {
         Context context{argv[0]};
-        Device device = context.create_device("cuda");
+        Device device = context.create_device(backend_name());
         Stream stream = device.create_stream(StreamTag::COMPUTE);
         return run_scene(argv[1], argc > 3 ? (uint32_t)strtoul(argv[3], nullptr, 0) : 0xffu, device, stream);
     }
@@ -214,7 +220,7 @@ int main(int argc, char *argv[]) {
     auto tris = read_file<Triangle>(dir + "/tris.bin");
     LUISA_ASSERT(!verts.empty() && !tris.empty(), "missing verts.bin / tris.bin in {}", dir);
     Context context{argv[0]};
-    Device device = context.create_device("cuda");
+    Device device = context.create_device(backend_name());
     Stream stream = device.create_stream(StreamTag::COMPUTE);
     Buffer<float4> vertex_buffer = device.create_buffer<float4>(verts.size());
     Buffer<Triangle> triangle_buffer = device.create_buffer<Triangle>(tris.size());
@@ -245,7 +251,7 @@ int main(int argc, char *argv[]) {
     auto closest = device.compile(closest_kernel);
     auto any = device.compile(any_kernel);
 
-    std::string json = "{\"backend\": \"cuda (OptiX)\", \"triangles\": " + std::to_string(tris.size()) + ", \"mesh_build_ms\": " + std::to_string(build_ms);
+    std::string json = "{\"backend\": \"" + std::string{backend_name()} + "\", \"triangles\": " + std::to_string(tris.size()) + ", \"mesh_build_ms\": " + std::to_string(build_ms);
     for (const char *name : {"primary", "bounce"}) {
         auto rays = read_file<Ray>(dir + "/rays_" + name + ".bin");
         if (rays.empty()) continue;
