@@ -150,7 +150,7 @@ def cpu_baseline(verts, tris, primary, bounce, sample: int, threads: int = 0) ->
             "note": "scalar double-precision CPU restatement of the Embree-backed reference path; real Embree (AVX-512 BVH8) would be several x faster"}
 
 
-def reference_gpu(verts, tris, primary, bounce) -> dict:
+def reference_gpu(verts, tris, primary, bounce, backend: str = "cuda") -> dict:
     """The REFERENCE's own GPU path on the same scene and rays, in the same run: LuisaCompute's `cuda` backend (OptiX,
     which is driver software traversal on B200) through baseline/_ref/bin/ref_optix_bench (baseline/ref_optix_bench.cpp: a
     DSL kernel calling accel.intersect over the ray buffer; unmodified reference sources, see
@@ -161,8 +161,8 @@ def reference_gpu(verts, tris, primary, bounce) -> dict:
     import tempfile
     bindir = os.path.join(ROOT, "baseline", "_ref", "bin")
     exe = os.path.join(bindir, "ref_optix_bench")
-    if not (os.path.exists(exe) and os.path.exists(os.path.join(bindir, "liblc-backend-cuda.so"))):
-        return {"unavailable": "baseline/_ref/bin/ref_optix_bench or liblc-backend-cuda.so not present"}
+    if not (os.path.exists(exe) and os.path.exists(os.path.join(bindir, f"liblc-backend-{backend}.so"))):
+        return {"unavailable": f"baseline/_ref/bin/ref_optix_bench or liblc-backend-{backend}.so not present"}
     d = tempfile.mkdtemp(prefix="lc_ref_")
     try:
         v4 = np.zeros((len(verts), 4), dtype=np.float32)
@@ -171,7 +171,7 @@ def reference_gpu(verts, tris, primary, bounce) -> dict:
         np.ascontiguousarray(tris, dtype=np.uint32).tofile(os.path.join(d, "tris.bin"))
         primary.tofile(os.path.join(d, "rays_primary.bin"))
         bounce.tofile(os.path.join(d, "rays_bounce.bin"))
-        env = dict(os.environ, LD_LIBRARY_PATH=bindir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+        env = dict(os.environ, LD_LIBRARY_PATH=bindir + ":" + os.environ.get("LD_LIBRARY_PATH", ""), LC_BACKEND=backend)
         r = subprocess.run([exe, d], capture_output=True, text=True, timeout=600, env=env)
         path = os.path.join(d, "ref_result.json")
         if r.returncode != 0 or not os.path.exists(path):
@@ -179,7 +179,9 @@ def reference_gpu(verts, tris, primary, bounce) -> dict:
         res = json.load(open(path))
         n = res["primary"]["rays"] + res["bounce"]["rays"]
         ms = res["primary"]["closest_ms"] + res["bounce"]["closest_ms"]
-        return {"what": "LuisaCompute cuda backend (OptiX) on this GPU, same scene and rays, DSL kernel accel.intersect per ray; best of 10, host clock "
+        what = ("LuisaCompute cuda backend (OptiX) on this GPU" if backend == "cuda" else
+                "lc-backend-b200 (the reference's CUDA backend with this repository's accel classes and device-library RT section, plugin/hybrid/)")
+        return {"what": what + ", same scene and rays, DSL kernel accel.intersect per ray through the reference's runtime API; best of 10, host clock "
                         "around dispatch + synchronize", "value": n / ms / 1e3, "unit": "Mrays/s",
                 "coherent_closest_mrays_s": res["primary"]["closest_mrays_s"], "incoherent_closest_mrays_s": res["bounce"]["closest_mrays_s"],
                 "incoherent_any_mrays_s": res["bounce"]["any_mrays_s"], "mesh_build_ms": res["mesh_build_ms"],
@@ -441,6 +443,7 @@ def main():
         if not args.no_cpu_baseline:
             cpu = cpu_baseline(verts, tris, primary, bounce, args.cpu_sample)
         ref_gpu = reference_gpu(verts, tris, primary, bounce) if (world == 1 and not args.no_reference_gpu) else None
+        dropin = reference_gpu(verts, tris, primary, bounce, backend="b200") if (world == 1 and not args.no_reference_gpu) else None
         hit_frac_p = float(np.mean(hp["inst"] != 0xFFFFFFFF))
         line = {
             "metric": "closest-hit ray throughput (coherent primary + incoherent bounce)", "value": value, "unit": "Mrays/s", "n_gpus": world,
@@ -456,7 +459,7 @@ def main():
                        "blas_build_ms": build_ms, "blas_build_mtris_s": (ntris / (build_ms * 1e-3) / 1e6) if build_ms else None,
                        "numa_binding": list(numa) if numa else None, "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
                        "scene_gen_s": gen_s},
-            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "e2e": e2e, "clocks": clocks,
+            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin_backend": dropin, "e2e": e2e, "clocks": clocks,
             "gpu_launches": 4 * K,  # per step: k_trace + k_refine_hits for the primary batch and for the bounce batch
         }
         print(json.dumps(line))
