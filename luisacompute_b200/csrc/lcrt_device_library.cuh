@@ -163,7 +163,7 @@ __device__ inline const BlobHeader *devlib_tlas(LCAccel accel) noexcept { return
     lcrt::NoCallbacks cb;
     lcrt::Traversal<lcrt::MODE_CLOSEST, false, lcrt::LocalStore, lcrt::NoCallbacks> tr;
     tr.init(lcrt::devlib_tlas(accel), reinterpret_cast<const lcrt::Instance *>(accel.instances), reinterpret_cast<const lcrt::Ray *>(&ray), mask, &store, &cb);
-    while (tr.step()) {}
+    tr.run();
     LCTriangleHit hit;
     lc_uint type;
     tr.result(hit.m0, hit.m1, type, hit.m3, hit.m2.x, hit.m2.y);
@@ -175,7 +175,7 @@ __device__ inline const BlobHeader *devlib_tlas(LCAccel accel) noexcept { return
     lcrt::NoCallbacks cb;
     lcrt::Traversal<lcrt::MODE_ANY, false, lcrt::LocalStore, lcrt::NoCallbacks> tr;
     tr.init(lcrt::devlib_tlas(accel), reinterpret_cast<const lcrt::Instance *>(accel.instances), reinterpret_cast<const lcrt::Ray *>(&ray), mask, &store, &cb);
-    while (tr.step()) {}
+    tr.run();
     return tr.has_hit();
 }
 
@@ -346,7 +346,7 @@ __device__ inline void lc_ray_query_trace(LCRayQuery &q, lc_uint impl_tag, void 
     tr.init(lcrt::devlib_tlas(q.accel), reinterpret_cast<const lcrt::Instance *>(q.accel.instances), reinterpret_cast<const lcrt::Ray *>(&q.ray), q.mask,
             &store, &cb);
     tr.terminate_on_first = (q.flags & LC_RAY_FLAG_TERMINATE_ON_FIRST_HIT) != 0u;
-    while (tr.step()) {}
+    tr.run();
     tr.result(q.hit.m0, q.hit.m1, q.hit.m3, q.hit.m4, q.hit.m2.x, q.hit.m2.y);
     if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
 }

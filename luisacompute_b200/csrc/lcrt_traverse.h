@@ -608,6 +608,12 @@ struct Traversal {
     // vote on when the (poorly converged) primitive phase is worth running.  Both return true while there is more work.
     LCRT_HD bool prim_pending() const { return Gt.y != 0u; }
     LCRT_HD bool step() { return step_node() && step_prim(); }
+    // whole ray, for the inline entry points (one thread, one ray, no refill).  One node, then one primitive per
+    // iteration; the "while-while" alternative (nodes until a primitive group turns up, then the whole group) measured
+    // 27 % slower on coherent and 18 % slower on incoherent rays through lc-backend-b200 (C2, B200).
+    LCRT_HD void run() {
+        while (step()) {}
+    }
 
     LCRT_HD bool step_node() {
         if (done) return false;
