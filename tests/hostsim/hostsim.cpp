@@ -36,7 +36,7 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
         Node8 nd;
         memset(&nd, 0, sizeof(nd));
         Box nb = box_empty();
-        Box sb[8];
+        Box sb[8] = {};
         bool sv[8] = {};
         quantize_node(nd, nb, sb, sv);
         nodes[0] = nd;
