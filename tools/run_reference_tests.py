@@ -63,7 +63,7 @@ def main():
     a = ap.parse_args()
     env = dict(os.environ, LD_LIBRARY_PATH=BIN + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
     res = {}
-    for test in ("test_rtx", "test_procedural"):
+    for test in ("test_rtx", "test_procedural", "test_procedural_callable", "test_indirect_rtx"):
         exe = os.path.join(BIN, test)
         if not os.path.exists(exe):
             res[test] = {"unavailable": "not built"}
