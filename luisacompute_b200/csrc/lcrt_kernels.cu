@@ -475,7 +475,10 @@ __global__ void k_update_handles(Instance *instances, const InstanceHandleUpdate
 #endif
 constexpr int TRACE_BLOCK = LCRT_TRACE_BLOCK;
 constexpr int TRACE_SMEM_STACK = 8;   // stack entries per thread kept in shared memory
-constexpr uint32_t TRACE_BATCH = 128; // rays a warp reserves per atomic
+#ifndef LCRT_TRACE_BATCH
+#define LCRT_TRACE_BATCH 128
+#endif
+constexpr uint32_t TRACE_BATCH = LCRT_TRACE_BATCH; // rays a warp reserves per atomic
 #ifndef LCRT_TRACE_MIN_BLOCKS
 #define LCRT_TRACE_MIN_BLOCKS 5     // resident blocks per SM the register allocation is bounded for
 #endif
