@@ -48,6 +48,7 @@ int main(int argc, char *argv[]) {
     const char *backend = getenv("LC_BACKEND") ? getenv("LC_BACKEND") : "cuda";
     // shadow rays end at d_light * C5_SHADOW_TMAX_SCALE (default 1: the integrator as specified).  Rays that end within rounding of
     // the light quad are where backends may legitimately differ (t <= t_max decided exactly vs in fp32); see tools/ref_optix_c5.py
+    const bool flat_loop = getenv("C5_FLAT_LOOP") && atoi(getenv("C5_FLAT_LOOP")) != 0;
     const float shadow_scale = getenv("C5_SHADOW_TMAX_SCALE") ? (float)atof(getenv("C5_SHADOW_TMAX_SCALE")) : 1.0f;
     std::vector<uint8_t> raw;
     {
@@ -181,15 +182,20 @@ int main(int argc, char *argv[]) {
         const float3 light_emission = make_float3(17.f, 12.f, 4.f), light_normal = make_float3(0.f, -1.f, 0.f);
         const float light_area = 0.25f, inv_pi = 0.318309886f;
         auto handler = sphere_handler(boxes);
-        $for (s, spp) {
+        Var<Ray> ray = make_ray(make_float3(0.f), make_float3(0.f, 0.f, -1.f), 0.f, 0.f);
+        Float3 beta = def(make_float3(1.f));
+        Float pdf_bsdf = def(0.f);
+        auto camera_ray = [&] {
             Float rx = lcg(state), ry = lcg(state);
             Float px = (cast<float>(coord.x) + rx) / frame * 2.f - cast<float>(size.x) / frame;
             Float py = -((cast<float>(coord.y) + ry) / frame * 2.f - cast<float>(size.y) / frame);
             const float th = std::tan(0.5f * 38.0f * 0.01745329252f);
-            Var<Ray> ray = make_ray(make_float3(0.f, 0.f, 3.4f), normalize(make_float3(px * th, py * th, -1.f)), 0.f, std::numeric_limits<float>::max());
-            Float3 beta = def(make_float3(1.f));
-            Float pdf_bsdf = def(0.f);
-            $for (depth, 10u) {
+            ray = make_ray(make_float3(0.f, 0.f, 3.4f), normalize(make_float3(px * th, py * th, -1.f)), 0.f, std::numeric_limits<float>::max());
+            beta = make_float3(1.f);
+            pdf_bsdf = 0.f;
+        };
+        // one bounce; a `$break` leaves the innermost DSL loop of the caller with path_ended still true
+        auto bounce = [&](UInt depth, Bool &path_ended) {
                 Var<CommittedHit> hit = accel.traverse(ray, {}).on_procedural_candidate(handler).trace();
                 rays += 1u;
                 $if (hit->miss()) { $break; };
@@ -249,8 +255,32 @@ int main(int argc, char *argv[]) {
                 Float q = max(l, 0.05f);
                 $if (lcg(state) >= q) { $break; };
                 beta *= 1.f / q;
-            };
+                path_ended = false;
         };
+        if (!flat_loop) {// the loop nest of src/tests/test_path_tracing.cpp:165-256
+            $for (s, spp) {
+                camera_ray();
+                $for (depth, 10u) {
+                    Bool path_ended = def(true);
+                    bounce(depth, path_ended);
+                };
+            };
+        } else {// one flat loop over (sample, bounce): a lane whose path ended starts its next sample at once; same random sequence, same sums
+            UInt s = def(0u), depth = def(0u);
+            $while (s < spp) {
+                $if (depth == 0u) { camera_ray(); };
+                Bool path_ended = def(true);
+                $loop {
+                    bounce(depth, path_ended);
+                    $break;
+                };
+                depth += 1u;
+                $if (path_ended | depth == 10u) {
+                    depth = 0u;
+                    s += 1u;
+                };
+            };
+        }
         seeds.write(pix, state);
         $if (any(isnan(radiance))) { radiance = make_float3(0.f); };
         Float4 acc = image.read(pix);

@@ -338,15 +338,27 @@ struct DevlibQueryCallbacks {
 
 }// namespace lcrt
 
-// cuda_device_resource.h:1941-1948: runs the query to completion and leaves the committed hit in q.hit
-__device__ inline void lc_ray_query_trace(LCRayQuery &q, lc_uint impl_tag, void *ctx) noexcept {
+// cuda_device_resource.h:1941-1948: runs the query to completion and leaves the committed hit in q.hit.
+// One out-of-line copy of the traversal serves every RayQuery site of the kernel (the handlers are selected by impl_tag at
+// run time, as the reference's __intersection__ / __anyhit__ programs do): a path tracer with a query_all and a query_any
+// site is 57 KB of SASS with a traversal per site, beyond the 32 KB L1.5 instruction cache, and spent 56 % of its
+// issue slots waiting for instructions.  LCRT_RAY_QUERY_INLINE=1 restores one specialised traversal per site.
+#ifndef LCRT_RAY_QUERY_INLINE
+#define LCRT_RAY_QUERY_INLINE 0
+#endif
+#if LCRT_RAY_QUERY_INLINE
+__device__ inline
+#else
+__device__ __noinline__
+#endif
+void lc_ray_query_trace(LCRayQuery &q, lc_uint impl_tag, void *ctx) noexcept {
     lcrt::LocalStore store;
     lcrt::DevlibQueryCallbacks cb{impl_tag, ctx};
     lcrt::Traversal<lcrt::MODE_QUERY, false, lcrt::LocalStore, lcrt::DevlibQueryCallbacks> tr;
     tr.init(lcrt::devlib_tlas(q.accel), reinterpret_cast<const lcrt::Instance *>(q.accel.instances), reinterpret_cast<const lcrt::Ray *>(&q.ray), q.mask,
             &store, &cb);
     tr.terminate_on_first = (q.flags & LC_RAY_FLAG_TERMINATE_ON_FIRST_HIT) != 0u;
-    tr.run();
+    tr.run_voting();
     tr.result(q.hit.m0, q.hit.m1, q.hit.m3, q.hit.m4, q.hit.m2.x, q.hit.m2.y);
     if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
 }

@@ -167,7 +167,7 @@ def c4(dev, n_tris, n_rays):
 
 
 def c5(dev, w=1920, h=1080, spp=16):
-    so = os.path.join(ROOT, "tools", "libc5pt.so")
+    so = os.environ.get("LCRT_C5_LIB", os.path.join(ROOT, "tools", "libc5pt.so"))
     L = C.CDLL(so)
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     L.c5_render.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, vp, vp, u32, u32, u32, u32, u32]

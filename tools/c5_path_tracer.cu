@@ -9,6 +9,9 @@
 
 #define LCRT_DEVLIB_STANDALONE
 #define LUISA_RAY_QUERY_IMPL_COUNT 2
+#ifndef C5_NESTED_LOOPS
+#define C5_NESTED_LOOPS 0
+#endif
 #include "../luisacompute_b200/csrc/lcrt_device_library.cuh"
 
 struct C5Params {
@@ -112,7 +115,7 @@ __device__ inline V3 offset_ray_origin(V3 p, V3 n) {
     return v3(one(p.x, n.x), one(p.y, n.y), one(p.z, n.z));
 }
 
-extern "C" __global__ void __launch_bounds__(256) k_c5_path_trace(C5Params params) {
+extern "C" __global__ void __launch_bounds__(256, 2) k_c5_path_trace(C5Params params) {
     const uint32_t x = blockIdx.x * 16u + (threadIdx.x & 15u), y = blockIdx.y * 16u + (threadIdx.x >> 4);
     if (x >= params.w || y >= params.h) return;
     const uint32_t pix = y * params.w + x;
@@ -125,15 +128,31 @@ extern "C" __global__ void __launch_bounds__(256) k_c5_path_trace(C5Params param
     const V3 light_emission = v3(17.f, 12.f, 4.f), light_normal = v3(0.f, -1.f, 0.f);
     const float light_area = 0.25f, inv_pi = 0.318309886f;
     LCRayQueryCtx0 ctx{params.aabbs};
+    // One flat loop over (sample, bounce): a lane whose path ended starts its next sample in the following iteration instead
+    // of idling until the longest path of the warp is done (nested loops reconverge after every sample: 6.3 of 32 lanes
+    // active on this scene, profiles/r1_c5_ncu.md).  The per-pixel random sequence and the order of the radiance sums are
+    // those of the nested loops, so the image is bit-identical.  C5_NESTED_LOOPS=1 builds the nested form.
+    LCRay ray;
+    V3 beta = v3(1.f, 1.f, 1.f);
+    float pdf_bsdf = 0.f;
+#if C5_NESTED_LOOPS
     for (uint32_t s = 0; s < params.spp; s++) {
-        const float rx = lcg(state), ry = lcg(state);
-        const float px = ((float)x + rx) / frame * 2.f - (float)params.w / frame, py = -(((float)y + ry) / frame * 2.f - (float)params.h / frame);
-        const V3 origin = v3(0.f, 0.f, 3.4f);
-        const float th = tanf(0.5f * 38.0f * 0.01745329252f);
-        LCRay ray = make_ray(origin, normalize(v3(px * th, py * th, -1.f)), 0.f, 3.402823466e38f);
-        V3 beta = v3(1.f, 1.f, 1.f);
-        float pdf_bsdf = 0.f;
         for (uint32_t depth = 0; depth < 10u; depth++) {
+#else
+    for (uint32_t s = 0, depth = 0; s < params.spp;) {
+        {
+#endif
+            if (depth == 0u) {
+                const float rx = lcg(state), ry = lcg(state);
+                const float px = ((float)x + rx) / frame * 2.f - (float)params.w / frame, py = -(((float)y + ry) / frame * 2.f - (float)params.h / frame);
+                const V3 origin = v3(0.f, 0.f, 3.4f);
+                const float th = tanf(0.5f * 38.0f * 0.01745329252f);
+                ray = make_ray(origin, normalize(v3(px * th, py * th, -1.f)), 0.f, 3.402823466e38f);
+                beta = v3(1.f, 1.f, 1.f);
+                pdf_bsdf = 0.f;
+            }
+            bool path_ended = true;
+            do {
             LCRayQueryAll q = lc_accel_query_all(params.accel, ray, 0xffu);
             {// ray query #0
                 lc_ray_query_trace(q, 0, &ctx);
@@ -199,6 +218,13 @@ extern "C" __global__ void __launch_bounds__(256) k_c5_path_trace(C5Params param
             const float qq = fmaxf(l, 0.05f);
             if (lcg(state) >= qq) break;
             beta = beta * (1.f / qq);
+            path_ended = false;
+            } while (false);
+#if C5_NESTED_LOOPS
+            if (path_ended) break;
+#else
+            if (path_ended || ++depth == 10u) depth = 0u, s++;
+#endif
         }
     }
     params.seeds[pix] = state;

@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--spp", type=int, default=16)
     ap.add_argument("--dir", default="/tmp/lc_ref_c5")
+    ap.add_argument("--flat", action="store_true", help="the program's flat (sample, bounce) loop instead of the nested loops")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "ref_optix_c5.json"))
     a = ap.parse_args()
     os.makedirs(a.dir, exist_ok=True)
@@ -46,10 +47,11 @@ def main():
         f.write(ALBEDO.tobytes())
         f.write(struct.pack("<I", len(meshes) - 1))
     env = dict(os.environ, LD_LIBRARY_PATH=BIN + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
-    res, imgs = {"workload": f"C5 Cornell room + 64 procedural spheres via RayQuery handlers, {a.width}x{a.height}, {a.spp} spp per dispatch, depth <= 10, DSL program"}, {}
+    res, imgs = {"workload": f"C5 Cornell room + 64 procedural spheres via RayQuery handlers, {a.width}x{a.height}, {a.spp} spp per dispatch, depth <= 10, DSL program, " +
+           ("one flat loop over (sample, bounce)" if a.flat else "nested sample / bounce loops")}, {}
     for backend in ("cuda", "b200"):
         r = subprocess.run([os.path.join(BIN, "c5_dsl_path_tracer"), a.dir, str(a.width), str(a.height), str(a.spp), "3"], capture_output=True, text=True,
-                           timeout=900, env=dict(env, LC_BACKEND=backend))
+                           timeout=900, env=dict(env, LC_BACKEND=backend, C5_FLAT_LOOP="1" if a.flat else "0"))
         line = [x for x in r.stdout.splitlines() if x.startswith("{")]
         if r.returncode != 0 or not line:
             res[backend] = {"unavailable": (r.stdout + r.stderr)[-1200:]}
