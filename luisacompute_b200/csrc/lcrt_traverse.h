@@ -631,6 +631,9 @@ struct Traversal {
     // backend the vote takes it from 287 to 410 spp/s.  A lane that loses a vote waits, so a latency-bound traversal of
     // one large mesh without refill loses (C2 through the drop-in backend: -16 %); closest / any-hit use run().
     // Lanes that are done keep voting until the group is, so the loop exit is uniform.
+    // Measured and rejected on top of this: entering a BLAS of <= 4 primitives without its root node test (record count in
+    // the instance record): C5 went from 411 to 364-372 spp/s, the extra set-up-only iterations and the lost box culling
+    // cost more than the node tests saved.
     LCRT_HD void run_voting() {
 #if defined(__CUDA_ARCH__) && LCRT_RUN_VOTE
         const uint32_t group = __activemask();

@@ -240,7 +240,7 @@ int hs_validate(const void *blob_, uint64_t *stats) {
 }
 
 // ---- tracing with the device traversal code -----------------------------------------------------------------
-// schedule of the two step halves: 0 = step() as the inline entry points do, 1 = the batch kernel's: step_prim() only
+// schedule of the two step halves: 0 = step() as the inline entry points do, 2 = run_voting() (RayQuery entry point), 1 = the batch kernel's: step_prim() only
 // runs when the warp votes for it, which from one lane's point of view is a pseudo-random delay of its primitive tests
 static int g_voted = 0;
 void hs_set_defer(int on) { g_voted = on; }
@@ -251,6 +251,23 @@ void run_ray(Tr &tr, uint64_t i) {
         return;
     }
     uint32_t lcg = (uint32_t)i * 2654435761u + 12345u;
+    if (g_voted == 2) {
+        // Traversal::run_voting() from one lane's point of view: each iteration the warp grants the node phase, the
+        // primitive phase or both; a phase the lane does not get is a delay.  Bounded, so that a schedule under which a
+        // lane can never progress fails the test instead of hanging it.
+        bool alive = true;
+        for (uint64_t it = 0; alive; it++) {
+            if (it > (1ull << 26)) {
+                fprintf(stderr, "hostsim: ray %llu makes no progress under the phase vote\n", (unsigned long long)i);
+                abort();
+            }
+            lcg = lcg * 1664525u + 1013904223u;
+            const bool run_node = (lcg >> 30) != 0u, run_prim = ((lcg >> 27) & 7u) < 5u || !run_node;
+            if (run_node && !tr.prim_pending()) alive = tr.step_node();
+            if (run_prim && alive && tr.prim_pending()) alive = tr.step_prim();
+        }
+        return;
+    }
     while (tr.step_node()) {
         lcg = lcg * 1664525u + 1013904223u;
         if ((lcg >> 29) < 3u && !tr.step_prim()) break;

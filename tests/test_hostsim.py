@@ -10,10 +10,11 @@ from luisacompute_b200 import scenes as S
 from tests.hostsim import hostsim_py as H
 
 
-@pytest.fixture(autouse=True, params=[0, 1], ids=["inline", "voted"])
+@pytest.fixture(autouse=True, params=[0, 1, 2], ids=["inline", "voted", "phase-voted"])
 def schedule(request):
     """Both schedules of the traversal: step() as the inline entry points run it, and the batch kernel's, where the
-    primitive half only runs when the warp votes for it (a pseudo-random delay from one lane's point of view)."""
+    primitive half only runs when the warp votes for it (a pseudo-random delay from one lane's point of view), and
+    run_voting()'s, where either half may be withheld."""
     H.lib().hs_set_defer(request.param)
     yield request.param
     H.lib().hs_set_defer(0)
