@@ -42,7 +42,7 @@ namespace lcrt {
 #define LCRT_RUN_NODE_VOTE 12
 #endif
 #ifndef LCRT_RUN_PRIM_VOTE
-#define LCRT_RUN_PRIM_VOTE 4
+#define LCRT_RUN_PRIM_VOTE 1// 1: the primitive phase runs whenever a lane waits for it (C5: 1 -> 420, 4 -> 409, 8 -> 407 spp/s)
 #endif
 
 struct TraceCounters {
@@ -625,7 +625,7 @@ struct Traversal {
     }
     // run() for traversals with expensive primitive phases (RayQuery candidates, many instance entries per ray): on the
     // device the lanes that entered together vote on the two phases of an iteration.  The primitive phase runs when
-    // LCRT_RUN_PRIM_VOTE lanes wait for it (as in the batch kernel); the node phase runs when LCRT_RUN_NODE_VOTE lanes, or
+    // LCRT_RUN_PRIM_VOTE lanes wait for it (default 1: always); the node phase runs when LCRT_RUN_NODE_VOTE lanes, or
     // at least as many lanes as wait for primitives, want it.  A path tracer over a small scene (36 triangles behind 9
     // instances, BASELINE config C5) ran the 289-instruction node test with 7 of 32 lanes under run(); through the drop-in
     // backend the vote takes it from 287 to 410 spp/s.  A lane that loses a vote waits, so a latency-bound traversal of
