@@ -284,7 +284,10 @@ struct alignas(16) BlobHeader {
     uint32_t prim_stride;
     uint64_t nodes_offset, prims_offset;
     uint64_t parent_offset, total_bytes;// parent_offset: u32 per node, (parent << 3) | slot, ~0 for the root
-    uint64_t reserved[4];
+    uint32_t plant_magic;// PLANT_MAGIC (lcrt_traverse.h): the inline entry points load it from here so that the compiler can
+                         // not fold it, see Traversal::init(const BlobHeader *, ...)
+    uint32_t reserved32;
+    uint64_t reserved[3];
 };
 static_assert(sizeof(BlobHeader) == 128, "BlobHeader must be 128 bytes");
 

@@ -38,6 +38,7 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
         memset(&hd, 0, sizeof(hd));
         hd.magic = BLOB_MAGIC, hd.kind = kind, hd.prim_count = n, hd.node_capacity = L.node_capacity;
         hd.flags = flags, hd.prim_stride = L.prim_stride;
+        hd.plant_magic = PLANT_MAGIC;
         hd.nodes_offset = L.nodes_offset, hd.prims_offset = L.prims_offset, hd.parent_offset = L.parent_offset, hd.total_bytes = L.total_bytes;
         for (int a = 0; a < 3; a++) hd.lo[a] = INFINITY, hd.hi[a] = -INFINITY;
         *h = hd;

@@ -455,6 +455,11 @@ struct Traversal {
         init(reinterpret_cast<const u4 *>(reinterpret_cast<const char *>(tlas) + tlas->nodes_offset),
              reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(tlas) + tlas->prims_offset), tlas->prim_count == 1u, instances_,
              ray, mask, store_, cb_);
+        // PRMT has one immediate operand.  With a compile-time magic the compiler spends it on the magic and keeps the four
+        // byte selectors in registers, which it re-materialises about 40 times per node test (301 instructions); a magic
+        // it can not see through goes into a register once and the selectors become immediates (as in the batch kernel,
+        // where it is a kernel parameter).
+        magic = tlas->plant_magic;
     }
 
     // ---- result (valid once step() has returned false).  hit_rec / hit_pi locate a surface hit for refine_surface_hit.

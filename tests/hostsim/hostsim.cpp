@@ -26,7 +26,7 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
     const BlobLayout L = blob_layout(Input::kind, n, flags);
     BlobHeader *h = reinterpret_cast<BlobHeader *>(blob);
     memset(h, 0, sizeof(BlobHeader));
-    h->magic = BLOB_MAGIC, h->kind = Input::kind, h->prim_count = n, h->node_capacity = L.node_capacity;
+    h->plant_magic = PLANT_MAGIC, h->magic = BLOB_MAGIC, h->kind = Input::kind, h->prim_count = n, h->node_capacity = L.node_capacity;
     h->flags = flags, h->prim_stride = L.prim_stride;
     h->nodes_offset = L.nodes_offset, h->prims_offset = L.prims_offset, h->parent_offset = L.parent_offset, h->total_bytes = L.total_bytes;
     for (int a = 0; a < 3; a++) h->lo[a] = INFINITY, h->hi[a] = -INFINITY;
