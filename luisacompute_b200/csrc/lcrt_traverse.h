@@ -137,8 +137,8 @@ LCRT_HD T ld16_stream(const T *p) {
 }
 
 // float whose mantissa carries byte `j` of `w` in bits 8..15: 2^23 + 256 * byte
-// `magic` must hold PLANT_MAGIC; it is passed in (from a kernel parameter) so that it lives in a uniform register and
-// the selector can be the instruction's immediate — as a literal, ptxas makes it the immediate and re-materialises
+// `magic` must hold PLANT_MAGIC; it is passed in (from a kernel parameter in the batch kernels, from the TLAS header in the
+// inline entry points) so that it lives in a register and the selector can be the instruction's immediate — as a literal, ptxas makes it the immediate and re-materialises
 // the selector into a register for every PRMT.
 constexpr uint32_t PLANT_MAGIC = 0x4B000000u;
 template<int J>
@@ -385,7 +385,7 @@ struct Traversal {
     Callbacks *cb;
     TraceCounters ctr;
     bool terminate_on_first = false;// query_any
-    uint32_t magic = PLANT_MAGIC;   // see plant_byte(); the batch kernel overwrites it with the same value from a kernel parameter
+    uint32_t magic = PLANT_MAGIC;   // see plant_byte(); overwritten with the same value from a kernel parameter / the TLAS header
     static constexpr uint32_t RAY_PENDING = 0xffffffffu;// octinv value: the current-space ray must be (re)derived
     LCRT_HD bool MODE_ANY_QUERY() const { return MODE == MODE_QUERY && terminate_on_first; }
 
