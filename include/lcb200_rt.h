@@ -52,7 +52,8 @@ enum {
     LCRT_ERROR_BUFFER_TOO_SMALL = -2,
     LCRT_ERROR_CUDA = -3,
     LCRT_ERROR_NOT_UPDATABLE = -4,
-    LCRT_ERROR_MISALIGNED = -5
+    LCRT_ERROR_MISALIGNED = -5,
+    LCRT_ERROR_BUILD_FAILED = -6 /* a build / refit / traversal flagged an error on the device (lcrtBlobInfo.error, .trace_error) */
 };
 
 enum { LCRT_KIND_TRIANGLES = 0, LCRT_KIND_AABBS = 1, LCRT_KIND_INSTANCES = 2 };
@@ -122,6 +123,10 @@ typedef struct lcrtBlobInfo {
     uint32_t built, error, flags, prim_stride;
     float lo[3], hi[3];
     uint64_t nodes_offset, prims_offset, total_bytes;
+    uint32_t depth;       /* BVH8 levels */
+    uint32_t max_stack;   /* TLAS: levels + 2 + deepest instanced BLAS = stack entries a ray can need (<= 96 or error 5) */
+    uint32_t trace_error; /* bit 0: a traversal ran out of stack on this TLAS (never on structures built by this library) */
+    uint32_t reserved;
 } lcrtBlobInfo;
 LCRT_API int lcrtBlobGetInfo(lcrtStream stream, const void *blob, lcrtBlobInfo *out);
 

@@ -72,7 +72,8 @@ class BlobInfo(C.Structure):
     _fields_ = [("kind", C.c_uint32), ("prim_count", C.c_uint32), ("node_count", C.c_uint32), ("node_capacity", C.c_uint32),
                 ("built", C.c_uint32), ("error", C.c_uint32), ("flags", C.c_uint32), ("prim_stride", C.c_uint32),
                 ("lo", C.c_float * 3), ("hi", C.c_float * 3), ("nodes_offset", C.c_uint64), ("prims_offset", C.c_uint64),
-                ("total_bytes", C.c_uint64)]
+                ("total_bytes", C.c_uint64), ("depth", C.c_uint32), ("max_stack", C.c_uint32), ("trace_error", C.c_uint32),
+                ("reserved", C.c_uint32)]
 
 
 class Sizes(C.Structure):

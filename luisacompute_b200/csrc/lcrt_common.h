@@ -286,8 +286,10 @@ struct alignas(16) BlobHeader {
     uint64_t parent_offset, total_bytes;// parent_offset: u32 per node, (parent << 3) | slot, ~0 for the root
     uint32_t plant_magic;// PLANT_MAGIC (lcrt_traverse.h): the inline entry points load it from here so that the compiler can
                          // not fold it, see Traversal::init(const BlobHeader *, ...)
-    uint32_t reserved32;
-    uint64_t reserved[3];
+    uint32_t trace_error;// set (atomicOr) by a traversal that had to give up on a ray: bit 0 = stack overflow (lcrt_traverse.h push())
+    uint32_t depth;      // BVH8 levels of this structure (device-written by the build)
+    uint32_t max_stack;  // TLAS: depth + 2 + deepest instanced BLAS depth = the most stack entries a ray can need; BLAS: depth
+    uint64_t reserved[2];
 };
 static_assert(sizeof(BlobHeader) == 128, "BlobHeader must be 128 bytes");
 

@@ -156,6 +156,10 @@ __device__ inline void lc_accel_set_instance_user_id(LCAccel accel, lc_uint inde
 // ------------------------------------------------------------------------------------------ intersect / intersect_any
 namespace lcrt {
 __device__ inline const BlobHeader *devlib_tlas(LCAccel accel) noexcept { return reinterpret_cast<const BlobHeader *>(accel.handle); }
+// a ray that ran out of traversal stack (never on a structure this library built: BlobHeader::max_stack) is reported, not hidden
+__device__ inline void devlib_report(LCAccel accel, bool overflowed) noexcept {
+    if (overflowed) atomicOr(&reinterpret_cast<BlobHeader *>(accel.handle)->trace_error, 1u);
+}
 }// namespace lcrt
 
 [[nodiscard]] __device__ inline LCTriangleHit lc_accel_trace_closest(LCAccel accel, LCRay ray, lc_uint mask) noexcept {
@@ -164,6 +168,7 @@ __device__ inline const BlobHeader *devlib_tlas(LCAccel accel) noexcept { return
     lcrt::Traversal<lcrt::MODE_CLOSEST, false, lcrt::LocalStore, lcrt::NoCallbacks> tr;
     tr.init(lcrt::devlib_tlas(accel), reinterpret_cast<const lcrt::Instance *>(accel.instances), reinterpret_cast<const lcrt::Ray *>(&ray), mask, &store, &cb);
     tr.run();
+    lcrt::devlib_report(accel, tr.overflowed());
     LCTriangleHit hit;
     lc_uint type;
     tr.result(hit.m0, hit.m1, type, hit.m3, hit.m2.x, hit.m2.y);
@@ -176,6 +181,7 @@ __device__ inline const BlobHeader *devlib_tlas(LCAccel accel) noexcept { return
     lcrt::Traversal<lcrt::MODE_ANY, false, lcrt::LocalStore, lcrt::NoCallbacks> tr;
     tr.init(lcrt::devlib_tlas(accel), reinterpret_cast<const lcrt::Instance *>(accel.instances), reinterpret_cast<const lcrt::Ray *>(&ray), mask, &store, &cb);
     tr.run();
+    lcrt::devlib_report(accel, tr.overflowed());
     return tr.has_hit();
 }
 
@@ -359,6 +365,7 @@ void lc_ray_query_trace(LCRayQuery &q, lc_uint impl_tag, void *ctx) noexcept {
             &store, &cb);
     tr.terminate_on_first = (q.flags & LC_RAY_FLAG_TERMINATE_ON_FIRST_HIT) != 0u;
     tr.run_voting();
+    lcrt::devlib_report(q.accel, tr.overflowed());
     tr.result(q.hit.m0, q.hit.m1, q.hit.m3, q.hit.m4, q.hit.m2.x, q.hit.m2.y);
     if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
 }

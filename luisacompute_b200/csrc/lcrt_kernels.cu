@@ -30,7 +30,9 @@ static_assert(SORT_TILE == SORT_TILE_KEYS, "lcrt_layout.h and lcrt_sort.cuh disa
 // =====================================================================================================================
 // build kernels
 // =====================================================================================================================
-enum SmallSlots : uint32_t { SM_CMIN = 0, SM_CMAX = 3, SM_ROOT = 6, SM_ABORT = 7, SM_COUNTERS = 8 /* nodes, prims, done */, SM_BARRIER = 11 /* arrivals, generation, node-count snapshots [2] */ };
+enum SmallSlots : uint32_t { SM_CMIN = 0, SM_CMAX = 3, SM_ROOT = 6, SM_ABORT = 7, SM_COUNTERS = 8 /* nodes, prims, done */, SM_BARRIER = 11 /* arrivals, generation, node-count snapshots [2] */,
+                           SM_LEVELS = 15 /* BVH8 levels the collapse processed */, SM_CHILD_DEPTH = 16 /* TLAS: deepest instanced BLAS */ };
+static_assert(SM_CHILD_DEPTH < SMALL_WORDS, "scratch words");
 
 __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t flags, BlobLayout L, uint32_t *small) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -47,6 +49,7 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
         small[SM_ROOT] = INVALID_U32, small[SM_ABORT] = 0u;
         small[SM_COUNTERS + 0] = 1u, small[SM_COUNTERS + 1] = 0u, small[SM_COUNTERS + 2] = 0u;
         small[SM_BARRIER + 0] = small[SM_BARRIER + 1] = small[SM_BARRIER + 2] = small[SM_BARRIER + 3] = 0u;
+        small[SM_LEVELS] = 0u, small[SM_CHILD_DEPTH] = 0u;
         if (n == 0u) {
             // an empty structure: one node with no children; nothing can be hit
             Node8 nd;
@@ -59,7 +62,7 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
             Node8 *nodes = reinterpret_cast<Node8 *>(reinterpret_cast<char *>(h) + L.nodes_offset);
             copy_vec16(&nodes[0], &nd, 5);
             if (L.parent_offset) *reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(h) + L.parent_offset) = INVALID_U32;
-            h->node_count = 1u, h->built = 1u;
+            h->node_count = 1u, h->built = 1u, h->depth = 1u, h->max_stack = 1u;
         }
     }
 }
@@ -350,7 +353,7 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
 // snapshots the node counter, which is the next level's `end`).  The grid never exceeds what is co-resident, so the
 // barrier can not deadlock; there is no polling on individual tasks.
 template<class Input>
-__global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *bar) {
+__global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *bar, uint32_t *levels_out) {
     __shared__ __align__(16) unsigned char node_smem[(COLLAPSE_BLOCK / 8) * sizeof(Node8)];
     const uint32_t octets = COLLAPSE_BLOCK / 8u;
     const uint32_t stride = gridDim.x * octets, goct = blockIdx.x * octets + (threadIdx.x >> 3);
@@ -401,20 +404,37 @@ __global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_co
         begin = end, end = s_end;
         __syncthreads();
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) levels_out[0] = gen;// one level per iteration: the depth of the wide hierarchy
 }
 
 template<class Input>
-__global__ void __launch_bounds__(256) k_emit_records(Bvh2 t, Bvh8Out o, Input in) {
+__global__ void __launch_bounds__(256) k_emit_records(Bvh2 t, Bvh8Out o, Input in, uint32_t *child_depth) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < t.n) emit_record(t, o, in, j);
+    if constexpr (Input::kind == KIND_INSTANCES) {
+        // deepest instanced BLAS (one atomic per warp): the TLAS header records the stack a ray can need
+        uint32_t d = 0u;
+        if (j < t.n) {
+            const BlobHeader *h = InstInput::blas_of(in.inst[t.order[o.rec_src[j]]]);
+            if (h) d = h->depth;
+        }
+        d = __reduce_max_sync(0xffffffffu, d);
+        if ((threadIdx.x & 31u) == 0u && d) atomicMax(child_depth, d);
+    }
 }
 
+// error codes in BlobHeader::error: 1 node capacity, 2 grid barrier gave up, 3 primitive count mismatch, 4 refit of a blob
+// that is not updatable, 5 the hierarchy is deeper than the traversal stack (LCRT_STACK_SIZE)
 __global__ void k_build_finalize(BlobHeader *h, const uint32_t *small, uint32_t n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         h->node_count = small[SM_COUNTERS + 0];
         h->prim_written = small[SM_COUNTERS + 1];
-        const bool ok = small[SM_ABORT] == 0u && small[SM_COUNTERS + 2] == n && small[SM_COUNTERS + 0] <= h->node_capacity;
-        h->error = ok ? 0u : (small[SM_ABORT] ? small[SM_ABORT] : 3u);
+        h->depth = small[SM_LEVELS];
+        h->max_stack = h->kind == KIND_INSTANCES ? small[SM_LEVELS] + 2u + small[SM_CHILD_DEPTH] : small[SM_LEVELS];
+        bool ok = small[SM_ABORT] == 0u && small[SM_COUNTERS + 2] == n && small[SM_COUNTERS + 0] <= h->node_capacity;
+        uint32_t err = ok ? 0u : (small[SM_ABORT] ? small[SM_ABORT] : 3u);
+        if (ok && h->max_stack > (uint32_t)LCRT_STACK_SIZE) ok = false, err = 5u;
+        h->error = err;
         h->built = ok ? 1u : 0u;
     }
 }
@@ -587,6 +607,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                     o[1] = make_u2(type == HIT_SURFACE ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(type, as_uint(tr.hit_t()));
                 }
                 if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts, c_exact += tr.ctr.exact;
+                if (tr.overflowed()) atomicOr(const_cast<uint32_t *>(&p.tlas->trace_error), 1u);
                 unsaved = false;
             }
             if (exhausted) break;// every lane idle and nothing left to fetch
@@ -781,12 +802,12 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
         const uint32_t need = (L.node_capacity + COLLAPSE_BLOCK / 8u - 1u) / (COLLAPSE_BLOCK / 8u);
         if (g > need) g = need;
         // cooperative launch: the runtime guarantees that all blocks are co-resident (the kernel has a grid barrier)
-        uint32_t *abort_flag = small + SM_ABORT, *bar = small + SM_BARRIER;
+        uint32_t *abort_flag = small + SM_ABORT, *bar = small + SM_BARRIER, *levels = small + SM_LEVELS;
         Input in_arg = in;
-        void *args[] = {&t, &o, &in_arg, &abort_flag, &bar};
+        void *args[] = {&t, &o, &in_arg, &abort_flag, &bar, &levels};
         LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(COLLAPSE_BLOCK), args, 0, stream));
     }
-    k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in);
+    k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in, small + SM_CHILD_DEPTH);
     LCRT_LAUNCH_CHECK("k_emit_records");
     k_build_finalize<<<1, 32, 0, stream>>>(h, small, n);
     LCRT_LAUNCH_CHECK("k_build_finalize");
@@ -873,6 +894,7 @@ const char *lcrtGetErrorString(int code) {
         case LCRT_ERROR_CUDA: return "CUDA error (see lcrtGetLastCudaError)";
         case LCRT_ERROR_NOT_UPDATABLE: return "acceleration structure was not built with LCRT_BUILD_ALLOW_UPDATE";
         case LCRT_ERROR_MISALIGNED: return "misaligned pointer";
+        case LCRT_ERROR_BUILD_FAILED: return "device-side build / refit / traversal error (see lcrtBlobInfo.error, .trace_error)";
         default: return "unknown error";
     }
 }
@@ -988,6 +1010,7 @@ int lcrtBlobGetInfo(lcrtStream stream, const void *blob, lcrtBlobInfo *out) {
     out->built = h.built, out->error = h.error, out->flags = h.flags, out->prim_stride = h.prim_stride;
     for (int a = 0; a < 3; a++) out->lo[a] = h.lo[a], out->hi[a] = h.hi[a];
     out->nodes_offset = h.nodes_offset, out->prims_offset = h.prims_offset, out->total_bytes = h.total_bytes;
+    out->depth = h.depth, out->max_stack = h.max_stack, out->trace_error = h.trace_error, out->reserved = 0u;
     return LCRT_SUCCESS;
 }
 

@@ -45,7 +45,7 @@ struct TempLayout {
 };
 
 constexpr uint32_t SORT_TILE = 4096;     // keys per block per pass (256 threads x 16)
-constexpr uint32_t SMALL_WORDS = 16;
+constexpr uint32_t SMALL_WORDS = 32;
 
 inline TempLayout temp_layout(uint32_t n, uint32_t node_capacity) {
     TempLayout t;

@@ -7,6 +7,7 @@
 // exist so that RayQuery can be exercised and parity-checked through the plain C-ABI.  The oracle implements the
 // same rules (oracle/oracle.cpp TriProgram / ProcProgram).
 #pragma once
+#include "lcrt_build.h"
 #include "lcrt_traverse.h"
 
 namespace lcrt {
@@ -49,8 +50,31 @@ struct BuiltinPrograms {
                 else if (t1 >= (double)wr.tmin && t1 < (double)wr.tmax) r.committed = true, r.t_hit = (float)t1;
             }
         } else if (proc_prog == PROC_BOX) {
-            // entry distance of the object-space box (world ray moved to object space in double)
-            r.committed = false;// evaluated by the caller-specific program in the device library tests
+            // the AABB itself: entry distance of the object-space box, the world ray moved to object space in double
+            // (oracle/oracle.cpp slab() + PROC_BOX: t = max(tmin, entry), committed iff the slabs overlap and tmin <= t < tmax)
+            double inv[12];
+            if (!invert_affine(instances[inst].affine, inv)) return r;
+            const double wo[3] = {wr.ox, wr.oy, wr.oz}, wd[3] = {wr.dx, wr.dy, wr.dz};
+            const double blo[3] = {lo.x, lo.y, lo.z}, bhi[3] = {hi.x, hi.y, hi.z};
+            double t0 = wr.tmin, t1 = wr.tmax;
+            bool ok = true;
+            for (int a = 0; a < 3; a++) {
+                const double o = inv[4 * a] * wo[0] + inv[4 * a + 1] * wo[1] + inv[4 * a + 2] * wo[2] + inv[4 * a + 3];
+                const double d = inv[4 * a] * wd[0] + inv[4 * a + 1] * wd[1] + inv[4 * a + 2] * wd[2];
+                const double id = 1.0 / d;
+                double ta = (blo[a] - o) * id, tb = (bhi[a] - o) * id;
+                if (ta != ta || tb != tb) {// 0 * inf: origin on the slab plane, direction parallel to it
+                    if (o < blo[a] || o > bhi[a]) ok = false;
+                    continue;
+                }
+                if (ta > tb) {
+                    const double s = ta;
+                    ta = tb, tb = s;
+                }
+                ta -= fabs(ta) * 1e-12, tb += fabs(tb) * 1e-12;
+                t0 = ta > t0 ? ta : t0, t1 = tb < t1 ? tb : t1;
+            }
+            if (ok && t0 <= t1 && t0 >= (double)wr.tmin && t0 < (double)wr.tmax) r.committed = true, r.t_hit = (float)t0;
         }
         return r;
     }

@@ -530,10 +530,21 @@ struct Traversal {
         octinv = RAY_PENDING;
     }
 
+    // Guarded push.  The builder bounds the stack need (TLAS levels + 2 + deepest BLAS levels, recorded in
+    // BlobHeader::depth / max_stack and checked by k_build_finalize), so the guard never fires on a structure this
+    // library built; on a foreign or corrupted blob it ends the ray and raises STACK_OVERFLOW (reported through
+    // BlobHeader::trace_error by the callers) instead of overrunning the per-ray storage.
+    static constexpr uint32_t STACK_OVERFLOW = 0x80000000u;// flag bit in ray_mask (the mask itself is 8 bits)
+    LCRT_HD bool overflowed() const { return (ray_mask & STACK_OVERFLOW) != 0u; }
+    LCRT_HD void push(u2 v) {
+        if (sp < LCRT_STACK_SIZE) store->store(sp++, v);
+        else ray_mask |= STACK_OVERFLOW, done = true;
+    }
+
     LCRT_HD void enter_instance(uint32_t rec_index, const u4 r3, const u4 r4) {
         // keep what is left of the TLAS groups below the BLAS frames
-        if (G.y & 0xff000000u) store->store(sp++, G);
-        if (Gt.y & 0xffu) store->store(sp++, make_u2(Gt.x, Gt.y & 0xffu));
+        if (G.y & 0xff000000u) push(G);
+        if (Gt.y & 0xffu) push(make_u2(Gt.x, Gt.y & 0xffu));
         Gt = make_u2(0u, 0u);
         blas_sp = sp;
         nodes = reinterpret_cast<const u4 *>(((uint64_t)r3.y << 32) | r3.x);
@@ -677,7 +688,7 @@ struct Traversal {
             const uint32_t base = G.x;
             G.y &= ~(1u << child_bit);
             const uint32_t imask_parent = G.y & 0xffu;
-            if (G.y & 0xff000000u) store->store(sp++, G);
+            if (G.y & 0xff000000u) push(G);
             const uint32_t slot = (uint32_t)(child_bit - 24) ^ octinv;
             const uint32_t rel = (uint32_t)popc(imask_parent & ~(0xffffffffu << slot));
             const uint32_t ni = base + rel;

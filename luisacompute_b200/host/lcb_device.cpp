@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -50,22 +51,44 @@ static uint32_t build_flags(const lcbAccelOption &o) {
     return f;
 }
 
+// What a resource needs from its device: stream-ordered release of device memory (no host stall on destroy), the
+// "some BLAS moved" epoch and the list of structures whose device-side build status has not been looked at yet.
+struct DeviceServices {
+    virtual ~DeviceServices() = default;
+    virtual void retire(void *p) = 0;      // free `p` once everything queued so far on the device's known streams is done
+    virtual void note_stream(cudaStream_t s) = 0;
+    std::atomic<uint64_t> blob_epoch{1};   // bumped whenever a primitive's blob changes address
+};
+
 struct Resource {
     enum class Tag { MESH, PROCEDURAL, ACCEL };
     Tag tag;
     lcbAccelOption option;
+    DeviceServices *dev;
     std::mutex mutex;
     void *blob = nullptr;
     uint64_t blob_bytes = 0;
     void *temp = nullptr;// kept between builds of the same size (test_rtx rebuilds every frame, test_rtx.cpp:122-139)
     uint64_t temp_bytes = 0;
     int last_build_kind = 0;
-    explicit Resource(Tag t, const lcbAccelOption &o) : tag{t}, option{o} {}
+    cudaEvent_t ready = nullptr;// recorded on the build stream after every build / import: consumers on other streams wait on it
+    bool check_pending = false; // built since its header was last read back (lcbSynchronize surfaces build errors)
+    Resource(Tag t, const lcbAccelOption &o, DeviceServices *d) : tag{t}, option{o}, dev{d} {}
     virtual ~Resource() {
-        if (blob) cudaFree(blob);
-        if (temp) cudaFree(temp);
+        // stream-ordered: the memory goes back to the pool when the work queued so far has passed (the reference frees with
+        // cuMemFree, an implicit device synchronisation)
+        if (blob) dev->retire(blob);
+        if (temp) dev->retire(temp);
+        if (ready) cudaEventDestroy(ready);
     }
     uint64_t native() const { return reinterpret_cast<uint64_t>(blob); }
+
+    int mark_ready(cudaStream_t stream) {
+        if (!ready) LCB_CUDA(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+        LCB_CUDA(cudaEventRecord(ready, stream));
+        check_pending = true;
+        return 0;
+    }
 
     int ensure(cudaStream_t stream, uint64_t need_blob, uint64_t need_temp) {
         if (blob_bytes < need_blob || blob_bytes > need_blob * 2 + (1u << 20)) {
@@ -73,6 +96,7 @@ struct Resource {
             blob = nullptr, blob_bytes = 0;
             LCB_CUDA(cudaMallocAsync(&blob, need_blob, stream));
             blob_bytes = need_blob;
+            dev->blob_epoch.fetch_add(1);
         }
         if (temp_bytes < need_temp || temp_bytes > need_temp * 2 + (1u << 20)) {
             if (temp) LCB_CUDA(cudaFreeAsync(temp, stream));
@@ -87,25 +111,26 @@ struct Resource {
 struct Primitive : Resource {
     using Resource::Resource;
     bool built = false;
+    bool blob_updatable = false;// the blob carries the parent array a refit needs (imported blobs may not)
 };
 
 struct Mesh final : Primitive {
     uint64_t vertex_buffer = 0, vertex_buffer_size = 0, vertex_stride = 0, triangle_buffer = 0, triangle_buffer_size = 0;
-    explicit Mesh(const lcbAccelOption &o) : Primitive{Tag::MESH, o} {}
+    Mesh(const lcbAccelOption &o, DeviceServices *d) : Primitive{Tag::MESH, o, d} {}
 
     int build(cudaStream_t stream, const lcbMeshBuildCommand &c) {
         std::scoped_lock lock{mutex};
         const uint64_t vb = c.vertex_buffer + c.vertex_buffer_offset, tb = c.triangle_buffer + c.triangle_buffer_offset;
-        // cuda_mesh.cpp:42-54
-        const bool requires_build = !built || !option.allow_update || c.request == LCB_BUILD_FORCE_BUILD || vb != vertex_buffer ||
+        if (c.vertex_stride < 12 || (c.vertex_stride % 4) != 0) {
+            fprintf(stderr, "[lcb200] invalid vertex stride %llu\n", (unsigned long long)c.vertex_stride);
+            return LCRT_ERROR_INVALID_VALUE;
+        }
+        // cuda_mesh.cpp:42-54; a blob without the parent array (imported from a build without allow_update) can not be refitted
+        const bool requires_build = !built || !option.allow_update || !blob_updatable || c.request == LCB_BUILD_FORCE_BUILD || vb != vertex_buffer ||
                                     c.vertex_buffer_size != vertex_buffer_size || c.vertex_stride != vertex_stride || tb != triangle_buffer ||
                                     c.triangle_buffer_size != triangle_buffer_size;
         vertex_buffer = vb, vertex_buffer_size = c.vertex_buffer_size, vertex_stride = c.vertex_stride;
         triangle_buffer = tb, triangle_buffer_size = c.triangle_buffer_size;
-        if (vertex_stride < 12 || (vertex_stride % 4) != 0) {
-            fprintf(stderr, "[lcb200] invalid vertex stride %llu\n", (unsigned long long)vertex_stride);
-            return LCRT_ERROR_INVALID_VALUE;
-        }
         const uint32_t n = (uint32_t)(triangle_buffer_size / 12u);// sizeof(Triangle), cuda_mesh.cpp:25-26
         const uint32_t flags = build_flags(option);
         lcrtSizes sz;
@@ -114,25 +139,26 @@ struct Mesh final : Primitive {
             LCB_CHECK(ensure(stream, sz.blob_bytes, sz.build_temp_bytes > sz.update_temp_bytes ? sz.build_temp_bytes : sz.update_temp_bytes));
             LCB_CHECK(lcrtBuildTriangles(stream, reinterpret_cast<const void *>(vb), vertex_stride, reinterpret_cast<const void *>(tb), n, flags, temp,
                                          temp_bytes, blob, blob_bytes));
-            built = true, last_build_kind = 1;
+            built = true, last_build_kind = 1, blob_updatable = option.allow_update != 0u;
         } else {
+            LCB_CHECK(ensure(stream, blob_bytes, sz.update_temp_bytes));// an imported blob arrives without scratch
             LCB_CHECK(lcrtRefitTriangles(stream, reinterpret_cast<const void *>(vb), vertex_stride, reinterpret_cast<const void *>(tb), n, temp,
                                          temp_bytes, blob));
             last_build_kind = 2;
         }
-        return 0;
+        return mark_ready(stream);
     }
 };
 
 struct ProceduralPrimitive final : Primitive {
     uint64_t aabb_buffer = 0, aabb_buffer_size = 0;
-    explicit ProceduralPrimitive(const lcbAccelOption &o) : Primitive{Tag::PROCEDURAL, o} {}
+    ProceduralPrimitive(const lcbAccelOption &o, DeviceServices *d) : Primitive{Tag::PROCEDURAL, o, d} {}
 
     int build(cudaStream_t stream, const lcbProceduralPrimitiveBuildCommand &c) {
         std::scoped_lock lock{mutex};
         const uint64_t ab = c.aabb_buffer + c.aabb_buffer_offset;
         // cuda_procedural_primitive.cpp:33-43
-        const bool requires_build = !built || !option.allow_update || c.request == LCB_BUILD_FORCE_BUILD || ab != aabb_buffer ||
+        const bool requires_build = !built || !option.allow_update || !blob_updatable || c.request == LCB_BUILD_FORCE_BUILD || ab != aabb_buffer ||
                                     c.aabb_buffer_size != aabb_buffer_size;
         aabb_buffer = ab, aabb_buffer_size = c.aabb_buffer_size;
         const uint32_t n = (uint32_t)(aabb_buffer_size / 24u);// sizeof(AABB), cuda_procedural_primitive.cpp:17-19
@@ -142,12 +168,13 @@ struct ProceduralPrimitive final : Primitive {
         if (requires_build) {
             LCB_CHECK(ensure(stream, sz.blob_bytes, sz.build_temp_bytes > sz.update_temp_bytes ? sz.build_temp_bytes : sz.update_temp_bytes));
             LCB_CHECK(lcrtBuildAabbs(stream, reinterpret_cast<const void *>(ab), n, flags, temp, temp_bytes, blob, blob_bytes));
-            built = true, last_build_kind = 1;
+            built = true, last_build_kind = 1, blob_updatable = option.allow_update != 0u;
         } else {
+            LCB_CHECK(ensure(stream, blob_bytes, sz.update_temp_bytes));
             LCB_CHECK(lcrtRefitAabbs(stream, reinterpret_cast<const void *>(ab), n, temp, temp_bytes, blob));
             last_build_kind = 2;
         }
-        return 0;
+        return mark_ready(stream);
     }
 };
 
@@ -157,36 +184,111 @@ static uint64_t next_pow2(uint64_t v) {
     return p;
 }
 
+using ResourceMap = std::unordered_map<uint64_t, std::shared_ptr<Resource>>;
+
 struct Accel final : Resource {
     void *instance_buffer = nullptr;
     uint64_t instance_buffer_size = 0;// bytes
     uint32_t initialised_instances = 0;
-    std::vector<const Primitive *> primitives;
+    // per instance: the primitive it refers to and the blob address the instance record currently holds
+    std::vector<Primitive *> primitives;
     std::vector<uint64_t> prim_handles;
+    // the distinct primitives the instances refer to, kept alive (shared ownership) while they do: destroying a mesh that an
+    // accel still instances can not leave a dangling pointer behind (the reference's CUDAAccel holds raw pointers)
+    struct Held {
+        std::shared_ptr<Primitive> prim;
+        uint32_t uses = 0;
+    };
+    std::unordered_map<uint64_t, Held> held;      // lcb handle -> primitive
+    std::unordered_map<Primitive *, uint64_t> held_key;
+    uint64_t epoch_seen = 0;                       // DeviceServices::blob_epoch at the last handle scan
     bool requires_rebuild = true;
     bool built = false;
-    explicit Accel(const lcbAccelOption &o) : Resource{Tag::ACCEL, o} {}
+    // modification upload staging, reused across builds (pinned host + device); `staged` guards the pinned half
+    Modification *h_mods = nullptr;
+    void *d_mods = nullptr;
+    uint32_t mods_capacity = 0;
+    cudaEvent_t staged = nullptr;
+    Accel(const lcbAccelOption &o, DeviceServices *d) : Resource{Tag::ACCEL, o, d} {}
     ~Accel() override {
-        if (instance_buffer) cudaFree(instance_buffer);
+        if (instance_buffer) dev->retire(instance_buffer);
+        if (d_mods) dev->retire(d_mods);
+        if (staged) {
+            cudaEventSynchronize(staged);
+            cudaEventDestroy(staged);
+        }
+        if (h_mods) cudaFreeHost(h_mods);
     }
 
-    int build(cudaStream_t stream, const lcbAccelBuildCommand &c, const std::unordered_map<uint64_t, std::unique_ptr<Resource>> &resources) {
+    void release(Primitive *p) {
+        auto k = held_key.find(p);
+        if (k == held_key.end()) return;
+        auto it = held.find(k->second);
+        if (it != held.end() && --it->second.uses == 0u) {
+            held.erase(it);
+            held_key.erase(k);
+        }
+    }
+
+    int stage_mods(cudaStream_t stream, uint32_t n) {
+        if (n > mods_capacity) {
+            if (staged) LCB_CUDA(cudaEventSynchronize(staged));
+            if (h_mods) LCB_CUDA(cudaFreeHost(h_mods));
+            if (d_mods) dev->retire(d_mods);
+            h_mods = nullptr, d_mods = nullptr, mods_capacity = 0;
+            const uint32_t cap = (uint32_t)next_pow2(n < 64u ? 64u : n);
+            LCB_CUDA(cudaMallocHost(reinterpret_cast<void **>(&h_mods), (size_t)cap * sizeof(Modification)));
+            LCB_CUDA(cudaMallocAsync(&d_mods, (size_t)cap * sizeof(Modification), stream));
+            mods_capacity = cap;
+        }
+        if (!staged) LCB_CUDA(cudaEventCreateWithFlags(&staged, cudaEventDisableTiming));
+        else LCB_CUDA(cudaEventSynchronize(staged));// the previous upload has left the pinned buffer (long ago, normally)
+        return 0;
+    }
+
+    int build(cudaStream_t stream, const lcbAccelBuildCommand &c, const ResourceMap &resources) {
         std::scoped_lock lock{mutex};
         const uint32_t instance_count = c.instance_count;
         if (instance_count == 0u) {// cuda_accel.cpp:159
             fprintf(stderr, "[lcb200] Instance count must be greater than 0.\n");
             return LCRT_ERROR_INVALID_VALUE;
         }
+        // ---- validate every modification before any state changes (an error leaves the accel as it was)
+        const uint32_t n = c.modification_count;
+        const Modification *in_mods = static_cast<const Modification *>(c.modifications);
+        if (n && !in_mods) return LCRT_ERROR_INVALID_VALUE;
+        std::unordered_map<uint64_t, std::shared_ptr<Primitive>> fresh;// primitives this batch introduces
+        {
+            uint64_t last_handle = ~0ull;
+            for (uint32_t k = 0; k < n; k++) {
+                const Modification &m = in_mods[k];
+                if (m.index >= instance_count) {
+                    fprintf(stderr, "[lcb200] modification index %u out of range\n", m.index);
+                    return LCRT_ERROR_INVALID_VALUE;
+                }
+                if ((m.flags & lcrt::MOD_PRIMITIVE) && m.primitive != last_handle) {
+                    last_handle = m.primitive;
+                    if (held.count(m.primitive) || fresh.count(m.primitive)) continue;
+                    auto it = resources.find(m.primitive);
+                    if (it == resources.end() || it->second->tag == Resource::Tag::ACCEL) {
+                        fprintf(stderr, "[lcb200] modification refers to an unknown primitive handle\n");
+                        return LCRT_ERROR_INVALID_VALUE;
+                    }
+                    fresh.emplace(m.primitive, std::static_pointer_cast<Primitive>(it->second));
+                }
+            }
+        }
         // ---- instance buffer growth to the next power of two, old contents preserved (cuda_accel.cpp:160-170)
         if (const uint64_t size = (uint64_t)instance_count * sizeof(lcrt::Instance); instance_buffer_size < size) {
             void *old = instance_buffer;
             const uint64_t new_size = next_pow2(size);
-            LCB_CUDA(cudaMallocAsync(&instance_buffer, new_size, stream));
+            void *grown = nullptr;
+            LCB_CUDA(cudaMallocAsync(&grown, new_size, stream));
             if (old) {
-                LCB_CUDA(cudaMemcpyAsync(instance_buffer, old, instance_buffer_size, cudaMemcpyDeviceToDevice, stream));
+                LCB_CUDA(cudaMemcpyAsync(grown, old, instance_buffer_size, cudaMemcpyDeviceToDevice, stream));
                 LCB_CUDA(cudaFreeAsync(old, stream));
             }
-            instance_buffer_size = new_size;
+            instance_buffer = grown, instance_buffer_size = new_size;
         }
         if (instance_count > initialised_instances) {
             // fresh slots start as identity / mask 0xff / opaque (accel.rs:284-295)
@@ -194,57 +296,69 @@ struct Accel final : Resource {
             initialised_instances = instance_count;
         }
         const bool instance_count_changed = primitives.size() != instance_count;
+        for (size_t i = instance_count; i < primitives.size(); i++)
+            if (primitives[i]) release(primitives[i]);// popped instances let go of their primitive
         primitives.resize(instance_count, nullptr);
         prim_handles.resize(instance_count, 0ull);
         // ---- upload the modifications and apply them (cuda_accel.cpp:176-240)
-        if (const uint32_t n = c.modification_count) {
-            std::vector<Modification> host(n);
-            memcpy(host.data(), c.modifications, (size_t)n * sizeof(Modification));
-            for (auto &m : host) {
-                if (m.index >= instance_count) {
-                    fprintf(stderr, "[lcb200] modification index %u out of range\n", m.index);
-                    return LCRT_ERROR_INVALID_VALUE;
-                }
-                if (m.flags & lcrt::MOD_PRIMITIVE) {
-                    requires_rebuild = true;
-                    auto it = resources.find(m.primitive);
-                    if (it == resources.end() || it->second->tag == Resource::Tag::ACCEL) {
-                        fprintf(stderr, "[lcb200] modification refers to an unknown primitive handle\n");
-                        return LCRT_ERROR_INVALID_VALUE;
+        if (n) {
+            LCB_CHECK(stage_mods(stream, n));
+            memcpy(h_mods, in_mods, (size_t)n * sizeof(Modification));
+            uint64_t last_handle = ~0ull;
+            Primitive *last_prim = nullptr;
+            for (uint32_t k = 0; k < n; k++) {
+                Modification &m = h_mods[k];
+                if (!(m.flags & lcrt::MOD_PRIMITIVE)) continue;
+                requires_rebuild = true;
+                if (m.primitive != last_handle) {
+                    last_handle = m.primitive;
+                    auto h = held.find(m.primitive);
+                    if (h == held.end()) {
+                        h = held.emplace(m.primitive, Held{fresh.at(m.primitive), 0u}).first;
+                        held_key.emplace(h->second.prim.get(), m.primitive);
                     }
-                    auto prim = static_cast<const Primitive *>(it->second.get());
-                    primitives[m.index] = prim;
-                    m.primitive = prim->native();
-                    prim_handles[m.index] = prim->native();
-                    if (prim->tag == Resource::Tag::PROCEDURAL) m.flags |= lcrt::MOD_PROCEDURAL;
+                    last_prim = h->second.prim.get();
+                }
+                if (primitives[m.index] != last_prim) {
+                    held.find(last_handle)->second.uses++;
+                    if (primitives[m.index]) release(primitives[m.index]);
+                    primitives[m.index] = last_prim;
+                }
+                m.primitive = last_prim->native();
+                prim_handles[m.index] = last_prim->native();
+                if (last_prim->tag == Resource::Tag::PROCEDURAL) m.flags |= lcrt::MOD_PROCEDURAL;
+            }
+            LCB_CUDA(cudaMemcpyAsync(d_mods, h_mods, (size_t)n * sizeof(Modification), cudaMemcpyHostToDevice, stream));
+            LCB_CUDA(cudaEventRecord(staged, stream));
+            LCB_CHECK(lcrtInstancesApplyMods(stream, instance_buffer, d_mods, n));
+        }
+        // ---- BLAS handles that changed through a rebuild without a modification (cuda_accel.cpp:244-258, 286-308): the
+        // reference scans every instance on every build; here the scan only runs when some primitive's blob has moved
+        // since the last one (DeviceServices::blob_epoch)
+        bool handles_changed = false;
+        if (const uint64_t epoch = dev->blob_epoch.load(); epoch != epoch_seen) {
+            epoch_seen = epoch;
+            std::vector<lcrt::InstanceHandleUpdate> changed;
+            for (uint32_t i = 0; i < instance_count; i++) {
+                if (primitives[i] != nullptr && primitives[i]->native() != prim_handles[i]) {
+                    changed.push_back({i, primitives[i]->native()});
+                    prim_handles[i] = primitives[i]->native();
                 }
             }
-            void *update_buffer = nullptr;
-            LCB_CUDA(cudaMallocAsync(&update_buffer, (size_t)n * sizeof(Modification), stream));
-            LCB_CUDA(cudaMemcpyAsync(update_buffer, host.data(), (size_t)n * sizeof(Modification), cudaMemcpyHostToDevice, stream));
-            LCB_CHECK(lcrtInstancesApplyMods(stream, instance_buffer, update_buffer, n));
-            LCB_CUDA(cudaFreeAsync(update_buffer, stream));
-            // `host` is pageable: the copy above has been staged by the runtime before cudaMemcpyAsync returned
-        }
-        // ---- BLAS handles that changed through a rebuild without a modification (cuda_accel.cpp:244-258, 286-308)
-        std::vector<lcrt::InstanceHandleUpdate> changed;
-        for (uint32_t i = 0; i < instance_count; i++) {
-            if (primitives[i] != nullptr && primitives[i]->native() != prim_handles[i]) {
-                changed.push_back({i, primitives[i]->native()});
-                prim_handles[i] = primitives[i]->native();
+            if (!changed.empty()) {
+                handles_changed = true;
+                void *dbuf = nullptr;
+                const size_t bytes = changed.size() * sizeof(lcrt::InstanceHandleUpdate);
+                LCB_CUDA(cudaMallocAsync(&dbuf, bytes, stream));
+                cudaError_t e = cudaMemcpyAsync(dbuf, changed.data(), bytes, cudaMemcpyHostToDevice, stream);// pageable: staged before it returns
+                int rc = e == cudaSuccess ? lcrtInstancesUpdateHandles(stream, instance_buffer, dbuf, (uint32_t)changed.size()) : LCRT_ERROR_CUDA;
+                cudaFreeAsync(dbuf, stream);
+                if (rc != 0) return rc;
             }
         }
         // cuda_accel.cpp:261-267
         requires_rebuild = requires_rebuild || c.request == LCB_BUILD_FORCE_BUILD || !option.allow_update || !built || instance_count_changed ||
-                           !changed.empty();
-        if (!changed.empty()) {
-            void *dbuf = nullptr;
-            const size_t bytes = changed.size() * sizeof(lcrt::InstanceHandleUpdate);
-            LCB_CUDA(cudaMallocAsync(&dbuf, bytes, stream));
-            LCB_CUDA(cudaMemcpyAsync(dbuf, changed.data(), bytes, cudaMemcpyHostToDevice, stream));
-            LCB_CHECK(lcrtInstancesUpdateHandles(stream, instance_buffer, dbuf, (uint32_t)changed.size()));
-            LCB_CUDA(cudaFreeAsync(dbuf, stream));
-        }
+                           handles_changed;
         if (!c.update_instance_buffer_only) {// cuda_accel.cpp:309-317
             const uint32_t flags = build_flags(option);
             lcrtSizes sz;
@@ -259,22 +373,60 @@ struct Accel final : Resource {
             }
             requires_rebuild = false;
         }
-        return 0;
+        return mark_ready(stream);
     }
 };
 
 }// namespace lcb
 
-struct lcbDevice {
+struct lcbDevice final : lcb::DeviceServices {
     int index = 0;
     std::mutex mutex;
-    std::unordered_map<uint64_t, std::unique_ptr<lcb::Resource>> resources;
+    lcb::ResourceMap resources;
+    // streams this device has seen work on (builds, traces): a destroyed resource's memory is released behind all of them
+    std::mutex stream_mutex;
+    std::vector<cudaStream_t> streams;
+    cudaStream_t reaper = nullptr;
+    cudaEvent_t reaper_event = nullptr;
     // end-to-end helper state
     static constexpr int STAGE_SLOTS = 4;
     cudaStream_t io_streams[STAGE_SLOTS] = {};
     void *stage_rays[STAGE_SLOTS] = {};
     void *stage_hits[STAGE_SLOTS] = {};
     uint64_t stage_capacity = 0;
+
+    void note_stream(cudaStream_t s) override {
+        std::scoped_lock lock{stream_mutex};
+        for (auto k : streams)
+            if (k == s) return;
+        streams.push_back(s);
+    }
+    void forget_stream(cudaStream_t s) {
+        std::scoped_lock lock{stream_mutex};
+        for (size_t i = 0; i < streams.size(); i++)
+            if (streams[i] == s) {
+                streams.erase(streams.begin() + (long)i);
+                return;
+            }
+    }
+    // the reaper stream waits for what is queued right now on every known stream, then frees: no host synchronisation
+    void retire(void *p) override {
+        if (!p) return;
+        cudaSetDevice(index);
+        std::scoped_lock lock{stream_mutex};
+        bool ok = reaper != nullptr || cudaStreamCreateWithFlags(&reaper, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && (reaper_event != nullptr || cudaEventCreateWithFlags(&reaper_event, cudaEventDisableTiming) == cudaSuccess);
+        for (size_t i = 0; ok && i < streams.size(); i++)
+            ok = cudaEventRecord(reaper_event, streams[i]) == cudaSuccess && cudaStreamWaitEvent(reaper, reaper_event, 0) == cudaSuccess;
+        if (ok && cudaFreeAsync(p, reaper) == cudaSuccess) return;
+        // a stream handle that is no longer valid, or memory that did not come from the pool: drain and free the plain way
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        if (cudaFreeAsync(p, nullptr) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(p);
+        }
+    }
 
     template<class T>
     T *find(uint64_t handle, lcb::Resource::Tag tag) {
@@ -292,14 +444,14 @@ struct lcbDevice {
     uint64_t add(const lcbAccelOption *option) {
         lcbAccelOption o{0u, 1u, 0u};// AccelOption defaults (resource.h:119-125)
         if (option) o = *option;
-        auto r = std::make_unique<T>(o);
+        auto r = std::make_shared<T>(o, this);
         const uint64_t handle = reinterpret_cast<uint64_t>(r.get());// the CUDA backend also uses object addresses
         std::scoped_lock lock{mutex};
         resources.emplace(handle, std::move(r));
         return handle;
     }
     void remove(uint64_t handle) {
-        std::unique_ptr<lcb::Resource> victim;
+        std::shared_ptr<lcb::Resource> victim;
         {
             std::scoped_lock lock{mutex};
             auto it = resources.find(handle);
@@ -308,8 +460,38 @@ struct lcbDevice {
             resources.erase(it);
         }
         cudaSetDevice(index);
-        cudaDeviceSynchronize();// the reference defers destruction to stream callbacks; this layer simply drains
-        victim.reset();
+        victim.reset();// last owner (no accel instances it): ~Resource retires the device memory in stream order
+    }
+    // device-side build status of everything built since the last look (called after a stream synchronisation)
+    int surface_build_errors() {
+        std::vector<std::shared_ptr<lcb::Resource>> todo;
+        {
+            std::scoped_lock lock{mutex};
+            for (auto &kv : resources)
+                if (kv.second->check_pending) todo.push_back(kv.second);
+        }
+        int rc = 0;
+        for (auto &r : todo) {
+            std::scoped_lock lock{r->mutex};
+            if (!r->check_pending || !r->blob || !r->ready) continue;
+            if (cudaEventQuery(r->ready) != cudaSuccess) {
+                cudaGetLastError();
+                continue;// built on another stream that is still running: next time
+            }
+            r->check_pending = false;
+            lcrt::BlobHeader h;
+            if (cudaMemcpy(&h, r->blob, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return LCRT_ERROR_CUDA;
+            if (h.magic != lcrt::BLOB_MAGIC || h.error != 0u || !h.built) {
+                fprintf(stderr, "[lcb200] acceleration structure %p: device-side build / refit error %u (built=%u)\n", (void *)r.get(), h.error,
+                        h.built);
+                rc = h.error == 4u ? LCRT_ERROR_NOT_UPDATABLE : LCRT_ERROR_BUILD_FAILED;
+            }
+            if (h.trace_error != 0u) {
+                fprintf(stderr, "[lcb200] acceleration structure %p: a traversal ran out of stack (trace_error=%u)\n", (void *)r.get(), h.trace_error);
+                rc = LCRT_ERROR_BUILD_FAILED;
+            }
+        }
+        return rc;
     }
 };
 
@@ -354,6 +536,11 @@ void lcbDeviceDestroy(lcbDevice *device) {
     cudaSetDevice(device->index);
     cudaDeviceSynchronize();
     device->resources.clear();
+    if (device->reaper) {
+        cudaStreamSynchronize(device->reaper);
+        cudaStreamDestroy(device->reaper);
+    }
+    if (device->reaper_event) cudaEventDestroy(device->reaper_event);
     for (int i = 0; i < lcbDevice::STAGE_SLOTS; i++) {
         if (device->stage_rays[i]) cudaFree(device->stage_rays[i]);
         if (device->stage_hits[i]) cudaFree(device->stage_hits[i]);
@@ -382,6 +569,7 @@ int lcbMeshBuild(lcbDevice *device, lcrtStream stream, const lcbMeshBuildCommand
     if (!command) return LCRT_ERROR_INVALID_VALUE;
     auto m = device->find<lcb::Mesh>(command->handle, lcb::Resource::Tag::MESH);
     if (!m) return LCRT_ERROR_INVALID_VALUE;
+    device->note_stream(static_cast<cudaStream_t>(stream));
     return m->build(static_cast<cudaStream_t>(stream), *command);
 }
 
@@ -390,6 +578,7 @@ int lcbProceduralPrimitiveBuild(lcbDevice *device, lcrtStream stream, const lcbP
     if (!command) return LCRT_ERROR_INVALID_VALUE;
     auto p = device->find<lcb::ProceduralPrimitive>(command->handle, lcb::Resource::Tag::PROCEDURAL);
     if (!p) return LCRT_ERROR_INVALID_VALUE;
+    device->note_stream(static_cast<cudaStream_t>(stream));
     return p->build(static_cast<cudaStream_t>(stream), *command);
 }
 
@@ -398,7 +587,8 @@ int lcbAccelBuild(lcbDevice *device, lcrtStream stream, const lcbAccelBuildComma
     if (!command) return LCRT_ERROR_INVALID_VALUE;
     auto a = device->find<lcb::Accel>(command->handle, lcb::Resource::Tag::ACCEL);
     if (!a) return LCRT_ERROR_INVALID_VALUE;
-    std::scoped_lock lock{device->mutex};// primitives must not be destroyed while the accel resolves them
+    device->note_stream(static_cast<cudaStream_t>(stream));
+    std::scoped_lock lock{device->mutex};// the resource table must not change while the accel resolves primitive handles
     return a->build(static_cast<cudaStream_t>(stream), *command, device->resources);
 }
 
@@ -434,6 +624,8 @@ int lcbTraceClosest(lcbDevice *device, lcrtStream stream, uint64_t accel, const 
     LCB_DEVICE_GUARD(device);
     auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
     if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    device->note_stream(static_cast<cudaStream_t>(stream));
+    a->check_pending = true;// a traversal can flag the TLAS header (trace_error)
     return lcrtTraceClosest(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, hits, counters);
 }
 
@@ -442,6 +634,8 @@ int lcbTraceAny(lcbDevice *device, lcrtStream stream, uint64_t accel, const void
     LCB_DEVICE_GUARD(device);
     auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
     if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    device->note_stream(static_cast<cudaStream_t>(stream));
+    a->check_pending = true;// a traversal can flag the TLAS header (trace_error)
     return lcrtTraceAny(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, occluded, counters);
 }
 
@@ -450,6 +644,8 @@ int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *r
     LCB_DEVICE_GUARD(device);
     auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
     if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    device->note_stream(static_cast<cudaStream_t>(stream));
+    a->check_pending = true;// a traversal can flag the TLAS header (trace_error)
     return lcrtQuery(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, terminate_on_first, tri_program, proc_program, hits);
 }
 
@@ -469,6 +665,15 @@ int lcbTraceClosestHost(lcbDevice *device, uint64_t accel, const void *host_rays
             if (!device->io_streams[i]) LCB_CUDA(cudaStreamCreateWithFlags(&device->io_streams[i], cudaStreamNonBlocking));
         }
         device->stage_capacity = chunk_rays;
+    }
+    // the internal streams start behind the builds this trace depends on (they may still be running on the caller's streams)
+    {
+        std::scoped_lock lock{a->mutex};
+        for (int i = 0; i < SLOTS; i++) {
+            if (a->ready) LCB_CUDA(cudaStreamWaitEvent(device->io_streams[i], a->ready, 0));
+            for (auto &kv : a->held)
+                if (kv.second.prim->ready) LCB_CUDA(cudaStreamWaitEvent(device->io_streams[i], kv.second.prim->ready, 0));
+        }
     }
     // SLOTS streams, SLOTS staging slots: chunk k's H2D / trace / D2H are ordered on stream k % SLOTS.  With four
     // chunks in flight the host->device copy engine always has the next chunk queued while earlier chunks are being
@@ -508,20 +713,34 @@ int lcbPrimitiveImport(lcbDevice *device, lcrtStream stream, uint64_t handle, co
     if (!r || r->tag == lcb::Resource::Tag::ACCEL || !src_device || bytes < sizeof(lcrt::BlobHeader)) return LCRT_ERROR_INVALID_VALUE;
     std::scoped_lock lock{r->mutex};
     auto st = static_cast<cudaStream_t>(stream);
+    device->note_stream(st);
+    // the header says what arrives (import is rare: one small synchronous read-back)
+    lcrt::BlobHeader h;
+    LCB_CUDA(cudaMemcpyAsync(&h, src_device, sizeof(h), cudaMemcpyDeviceToHost, st));
+    LCB_CUDA(cudaStreamSynchronize(st));
+    const uint32_t want = r->tag == lcb::Resource::Tag::MESH ? lcrt::KIND_TRIANGLES : lcrt::KIND_AABBS;
+    if (h.magic != lcrt::BLOB_MAGIC || !h.built || h.error != 0u || h.kind != want || h.total_bytes > bytes) {
+        fprintf(stderr, "[lcb200] lcbPrimitiveImport: not a built blob of this primitive kind (magic %08x, kind %u, built %u, error %u)\n", h.magic, h.kind,
+                h.built, h.error);
+        return LCRT_ERROR_INVALID_VALUE;
+    }
     if (r->blob) LCB_CUDA(cudaFreeAsync(r->blob, st));
     r->blob = nullptr, r->blob_bytes = 0;
     LCB_CUDA(cudaMallocAsync(&r->blob, bytes, st));
     r->blob_bytes = bytes;
+    device->blob_epoch.fetch_add(1);
     LCB_CUDA(cudaMemcpyAsync(r->blob, src_device, bytes, cudaMemcpyDeviceToDevice, st));
-    static_cast<lcb::Primitive *>(r)->built = true;
+    auto prim = static_cast<lcb::Primitive *>(r);
+    prim->built = true, prim->blob_updatable = h.parent_offset != 0ull;
     r->last_build_kind = 1;
-    return 0;
+    return r->mark_ready(st);
 }
 
 int lcbSynchronize(lcbDevice *device, lcrtStream stream) {
     LCB_DEVICE_GUARD(device);
     LCB_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    return 0;
+    // builds never stall the host, so their device-side status is looked at here, at the caller's own synchronisation point
+    return device->surface_build_errors();
 }
 
 int lcbDownload(lcbDevice *device, lcrtStream stream, uint64_t device_address, void *host, uint64_t bytes) {
@@ -564,6 +783,7 @@ void lcbStreamDestroy(lcbDevice *device, lcrtStream stream) {
     if (!device || !stream) return;
     cudaSetDevice(device->index);
     cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    device->forget_stream(static_cast<cudaStream_t>(stream));
     cudaStreamDestroy(static_cast<cudaStream_t>(stream));
 }
 int lcbCopyAsync(lcbDevice *device, lcrtStream stream, void *dst, const void *src, uint64_t bytes) {

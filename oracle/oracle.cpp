@@ -8,13 +8,21 @@
 // only as the checker / timed CPU baseline.  The product (luisacompute_b200)
 // never links, loads or calls anything here.
 //
-// PARITY UNPINNED: the reference's real oracle is Rust + Embree 4 (crate
-// embree_sys 0.1.11, git 6a0a591d..., src/rust/Cargo.lock:266-274) and can
-// not be built in this image (no cargo/rustc, no Embree, no network).  The
-// reference ships no golden vectors for this path.  This
-// file therefore restates the *published semantics* and is pinned only by
-// (i) closed-form answers (ray/triangle, ray/sphere; tests/test_oracle.py) and
-// (ii) an O(rays x prims) brute-force mode in this same file.
+// PARITY PINNED BY REFERENCE-RUN OUTPUTS (OptiX path), NOT BY EMBREE: the reference's CPU oracle is Rust + Embree 4
+// (crate embree_sys 0.1.11, git 6a0a591d..., src/rust/Cargo.lock:266-274) and can not be built in this image (no
+// cargo/rustc, no Embree, no network), and the reference ships no golden vectors for this path.
+// What pins this file instead:
+//   (i)   outputs of the reference itself: its unmodified CUDA/OptiX backend, built by
+//         baseline/build_reference_cuda_backend.sh and run on a B200, produced tests/golden/ref_optix_ico4.npz (level-4
+//         icosphere, intersect / intersect_any) and tests/golden/ref_optix_scene.npz (24 instances with rotations,
+//         masks, opaque / non-opaque meshes, procedural spheres; intersect, intersect_any, RayQuery with triangle and
+//         procedural handlers); tests/test_reference_golden.py checks this oracle against both on the CPU.  The
+//         vectors are small (12 288 rays each) and carry the reference's fp32 accuracy, so they are compared at
+//         t 5e-5..5e-4 relative and barycentrics 2e-2; hit / miss, occlusion, hit types and ids must match exactly;
+//   (ii)  closed-form answers (ray / triangle, ray / sphere; tests/test_oracle.py);
+//   (iii) the O(rays x prims) brute-force mode in this same file.
+// The 1e-5 / 1e-4 bar of BASELINE.json is therefore met against THIS restatement (double precision), and the
+// reference-run comparison holds at the reference's own accuracy.
 //
 // What it follows (all paths relative to /root/reference):
 //   src/rust/luisa_compute_backend_impl/src/cpu/accel.rs

@@ -21,6 +21,15 @@ using namespace lcrt;
 namespace {
 
 template<class Input>
+uint32_t deepest_blas(const Input &) { return 0u; }
+uint32_t deepest_blas(const InstInput &in) {
+    uint32_t deepest = 0;
+    for (uint32_t i = 0; i < in.n; i++)
+        if (const BlobHeader *b = InstInput::blas_of(in.inst[i])) deepest = std::max(deepest, b->depth);
+    return deepest;
+}
+
+template<class Input>
 int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
     const uint32_t n = in.n;
     const BlobLayout L = blob_layout(Input::kind, n, flags);
@@ -40,7 +49,7 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
         bool sv[8] = {};
         quantize_node(nd, nb, sb, sv);
         nodes[0] = nd;
-        h->node_count = 1, h->built = 1;
+        h->node_count = 1, h->built = 1, h->depth = 1, h->max_stack = 1;
         return 0;
     }
     // centroid bounds
@@ -86,9 +95,19 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
     Bvh8Out o{h, nodes, blob + L.prims_offset, L.parent_offset ? reinterpret_cast<uint32_t *>(blob + L.parent_offset) : nullptr, task.data(),
               rec_src.data(), counters, L.node_capacity};
     task[0] = root;
-    for (uint32_t w = 0; w < counters[0]; w++) {
-        if (task[w] == INVALID_U32) return -11;
-        if (!collapse_node(t, o, in, w, task[w])) return -12;
+    // level by level, as k_collapse does: the wide nodes allocated while one level is processed are the next level
+    uint32_t levels = 0;
+    for (uint32_t begin = 0, end = 1; begin < end; levels++) {
+        for (uint32_t w = begin; w < end; w++) {
+            if (task[w] == INVALID_U32) return -11;
+            if (!collapse_node(t, o, in, w, task[w])) return -12;
+        }
+        begin = end, end = counters[0];
+    }
+    h->depth = levels, h->max_stack = levels;
+    if (Input::kind == KIND_INSTANCES) {
+        h->max_stack = levels + 2u + deepest_blas(in);
+        if (h->max_stack > (uint32_t)LCRT_STACK_SIZE) return -15;
     }
     if (counters[2] != n || counters[1] != n) return -13;
     for (uint32_t j = 0; j < n; j++) {
@@ -235,6 +254,7 @@ int hs_validate(const void *blob_, uint64_t *stats) {
         if (seen[i] != 1u) return -9;
     for (uint32_t i = 0; i < h->node_count; i++)
         if (node_seen[i] != 1u) return -10;
+    if (h->depth != max_depth) return -16;// the recorded level count is the depth of the wide hierarchy
     if (stats) stats[0] = h->node_count, stats[1] = max_depth, stats[2] = leaf_slots, stats[3] = child_slots, stats[4] = (uint64_t)(sah * 1e3);
     return 0;
 }
