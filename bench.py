@@ -13,8 +13,12 @@ Workload (BASELINE.json configs[1], "C2"): displaced icosphere level 8 (1 310 72
 `--impl reference` times that CPU path alone on the same workload definition.
 
 Multi-GPU (torchrun, one rank per GPU): replicated scene — rank 0 builds the BLAS, NCCL-broadcasts the position-
-independent blob, every rank builds its own TLAS — and rays are sharded by 65 536-ray tiles round-robin; no collective
-in the timed region (weak scaling: every rank traces 8 388 608 rays per step).
+independent blob, every rank builds its own TLAS — and rays are sharded by 65 536-ray tiles round-robin.  The headline stays
+the C2 step with the per-GPU work fixed ("weak": every rank traces 8 388 608 rays per step), and for N > 1 the timed region
+INCLUDES gathering every rank's 24-byte hit records into ray order on rank 0 (NCCL send/recv over NVLink, chunk by chunk on
+a side stream while the next chunk is traced: luisacompute_b200.dist.HitGatherer).  `detail.c4_strong` is BASELINE config 4
+at every N (1 included): 50 M-triangle soup built on rank 0 and broadcast, the FIXED batch of 64 Mi rays tile-sharded over
+the ranks (strong scaling) with the same in-region gather.
 """
 from __future__ import annotations
 
@@ -46,6 +50,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the run of the reference's own CUDA/OptiX backend")
+    ap.add_argument("--no-c4", action="store_true", help="skip detail.c4_strong (BASELINE config 4: 50 M triangles, 64 Mi rays sharded over the ranks)")
+    ap.add_argument("--c4-tris", type=int, default=50_000_000)
+    ap.add_argument("--c4-rays", type=int, default=64 << 20)
     return ap.parse_args()
 
 
@@ -190,6 +197,135 @@ def reference_gpu(verts, tris, primary, bounce, backend: str = "cuda") -> dict:
         return {"unavailable": f"{type(e).__name__}: {e}"}
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+
+CHUNK_TILES = 8     # tiles per trace launch / gather in the multi-GPU step (512 Ki rays, 12.6 MB of hit records)
+
+
+def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
+    """BASELINE config 4, strong scaling: 50 M random triangles (built on rank 0, blob broadcast over NCCL), the fixed batch of
+    64 Mi uniform rays in 65 536-ray tiles dealt round-robin, hit records gathered into ray order on rank 0 inside the timed
+    region.  Geometry and rays are drawn on the device with torch (same distributions as scenes.triangle_soup / uniform_rays,
+    whose PCG32 streams the parity tests use at smaller sizes)."""
+    import torch
+    import torch.distributed as dist
+    from luisacompute_b200 import scenes as S
+    from luisacompute_b200.dist import HitGatherer
+    tdev = dev.torch_device
+    n_tris, n_rays = args.c4_tris, (args.c4_rays // (TILE * world)) * TILE * world
+    out = {"workload": f"C4 {n_tris} random triangles (s=0.004), {n_rays} uniform incoherent closest-hit rays in {TILE}-ray tiles round-robin over "
+                       f"{world} GPU(s), hits gathered to rank 0 in ray order inside the timed region", "scaling": "strong"}
+    mesh = dev.create_mesh()
+    if rank == 0:
+        g = torch.Generator(device=tdev).manual_seed(1234)
+        c = torch.rand((n_tris, 3), device=tdev, generator=g)
+        verts = torch.zeros((n_tris, 3, 4), dtype=torch.float32, device=tdev)
+        verts[:, 0, :3] = c
+        verts[:, 1, :3] = c + (torch.rand((n_tris, 3), device=tdev, generator=g) * 2 - 1) * 0.004
+        verts[:, 2, :3] = c + (torch.rand((n_tris, 3), device=tdev, generator=g) * 2 - 1) * 0.004
+        del c
+        tris = torch.arange(3 * n_tris, dtype=torch.int32, device=tdev).view(-1, 3)
+        mesh.set_buffers(verts.view(-1, 4), tris, 16)
+        mesh.build()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mesh.build(lc.FORCE_BUILD)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        info = mesh.info()
+        assert info.built == 1 and info.error == 0, (info.built, info.error)
+        out.update(build_ms=min(times), build_mtris_s=n_tris / min(times) / 1e3, bvh_nodes=int(info.node_count), bvh_bytes=int(info.total_bytes))
+    if world > 1:
+        blob = mesh.export_blob() if rank == 0 else None
+        nbytes = torch.tensor([blob.numel() if rank == 0 else 0], dtype=torch.int64, device=tdev)
+        dist.broadcast(nbytes, 0)
+        if rank != 0:
+            blob = torch.empty(int(nbytes.item()), dtype=torch.uint8, device=tdev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        dist.broadcast(blob, 0)
+        e1.record()
+        torch.cuda.synchronize()
+        out["bvh_broadcast_ms"] = e0.elapsed_time(e1)
+        if rank != 0:
+            mesh.import_blob(blob)
+        torch.cuda.synchronize()
+        del blob
+    acc = dev.create_accel()
+    acc.emplace_back(mesh)
+    acc.build()
+    # the same 64 Mi rays on every rank (same seed, same generator), of which it keeps its own tiles
+    g2 = torch.Generator(device=tdev).manual_seed(5678)
+    rays = torch.zeros((n_rays, 8), dtype=torch.float32, device=tdev)
+    rays[:, 0:3] = torch.rand((n_rays, 3), device=tdev, generator=g2)
+    z = 1 - 2 * torch.rand(n_rays, device=tdev, generator=g2)
+    ph = 2 * np.pi * torch.rand(n_rays, device=tdev, generator=g2)
+    r = torch.sqrt(torch.clamp(1 - z * z, min=0))
+    rays[:, 4], rays[:, 5], rays[:, 6] = r * torch.cos(ph), r * torch.sin(ph), z
+    rays[:, 7] = 3.4028234663852886e38
+    del z, ph, r
+    n_tiles_local = n_rays // (TILE * world)
+    local = rays.view(n_tiles_local, world, TILE * 8)[:, rank].contiguous().view(-1) if world > 1 else rays.view(-1)
+    del rays
+    n_local = n_tiles_local * TILE
+    hits = torch.empty((n_local, 6), dtype=torch.int32, device=tdev)
+    gat = HitGatherer(n_tiles_local, tdev, chunk_tiles=2 * CHUNK_TILES) if world > 1 else None
+    lb = local.view(torch.uint8)
+    ct = 2 * CHUNK_TILES
+
+    def step():
+        for t0 in range(0, n_tiles_local, ct):
+            t1 = min(t0 + ct, n_tiles_local)
+            acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
+            if gat is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                gat.submit(hits[t0 * TILE:t1 * TILE], t0, t1, ev)
+        if gat is not None:
+            gat.finish()
+    step()
+    barrier()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / reps
+    # the trace alone (no gather), same chunking
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record()
+    for t0 in range(0, n_tiles_local, ct):
+        t1 = min(t0 + ct, n_tiles_local)
+        acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
+    t1e.record()
+    torch.cuda.synchronize()
+    trace_ms = t0e.elapsed_time(t1e)
+    if world > 1:
+        t = torch.tensor([ms, trace_ms], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, trace_ms = (float(x) for x in t.cpu())
+        # verification: every rank's records are where ray order puts them
+        chk = torch.stack([hits[:, 0].long().sum(), hits[:, 1].long().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)] if rank == 0 else None
+        dist.gather(chk, allc, 0)
+        if rank == 0:
+            fb = gat.full.view(n_tiles_local, world, TILE, 6)
+            for rr in range(world):
+                assert int(fb[:, rr, :, 0].long().sum()) == int(allc[rr][0]) and int(fb[:, rr, :, 1].long().sum()) == int(allc[rr][1]), f"gather mismatch, rank {rr}"
+            assert torch.equal(fb[:, 0].reshape(-1, 6), hits)
+    out.update(ms_per_step=ms, mrays_s=n_rays / ms / 1e3, trace_only_ms=trace_ms, trace_only_mrays_s=n_rays / trace_ms / 1e3,
+               gather_bytes_per_step=(world - 1) * n_local * 24 if world > 1 else 0, hit_fraction=float((hits[:, 0] != -1).float().mean().item()))
+    del gat, hits, local, lb, acc, mesh
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):
@@ -339,10 +475,35 @@ def main():
     bytes_b = 32 + 24 + cb[0] * 80 + cb[1] * 48 + cb[2] * 80
 
     # ------------------------------------------------------------------ timed region
+    # N = 1: one launch per batch.  N > 1: the same rays in chunks of CHUNK_TILES tiles, each chunk's hit records gathered
+    # into ray order on rank 0 (side stream) while the next chunk is traced; the step ends when the gather has.
     K, W = args.steps, max(args.warmup, 3)
+    gat_p = gat_b = None
+    n_tiles = n // TILE
+    if world > 1:
+        from luisacompute_b200.dist import HitGatherer
+        assert n % TILE == 0
+        gat_p, gat_b = HitGatherer(n_tiles, tdev, chunk_tiles=CHUNK_TILES), HitGatherer(n_tiles, tdev, chunk_tiles=CHUNK_TILES)
+
+    def trace_batch(d_rays, d_hits, gat):
+        if gat is None:
+            acc.trace_closest(d_rays, out=d_hits)
+            return
+        for t0 in range(0, n_tiles, CHUNK_TILES):
+            t1 = min(t0 + CHUNK_TILES, n_tiles)
+            acc.trace_closest(d_rays[t0 * TILE * 32:t1 * TILE * 32], out=d_hits[t0 * TILE:t1 * TILE])
+            e = torch.cuda.Event()
+            e.record()
+            gat.submit(d_hits[t0 * TILE:t1 * TILE], t0, t1, e)
+
+    def end_step():
+        if gat_p is not None:
+            gat_p.finish(), gat_b.finish()
+
     for _ in range(W):
-        acc.trace_closest(d_primary, out=d_hits_p)
-        acc.trace_closest(d_bounce, out=d_hits_b)
+        trace_batch(d_primary, d_hits_p, gat_p)
+        trace_batch(d_bounce, d_hits_b, gat_b)
+        end_step()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -351,19 +512,45 @@ def main():
     barrier()
     for k in range(K):
         ev[k][0].record()
-        acc.trace_closest(d_primary, out=d_hits_p)
+        trace_batch(d_primary, d_hits_p, gat_p)
         ev[k][1].record()
-        acc.trace_closest(d_bounce, out=d_hits_b)
+        trace_batch(d_bounce, d_hits_b, gat_b)
+        end_step()
         ev[k][2].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0][0].elapsed_time(ev[K - 1][2])
     tp_ms = float(np.mean([ev[k][0].elapsed_time(ev[k][1]) for k in range(K)]))
     tb_ms = float(np.mean([ev[k][1].elapsed_time(ev[k][2]) for k in range(K)]))
+    gather_ms = None
     if world > 1:
         t = torch.tensor([total_ms, tp_ms, tb_ms], dtype=torch.float64, device=tdev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, tp_ms, tb_ms = (float(x) for x in t.cpu())
+        # the gather by itself (nothing to hide behind): one batch, all chunks
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for t0 in range(0, n_tiles, CHUNK_TILES):
+            t1 = min(t0 + CHUNK_TILES, n_tiles)
+            gat_b.submit(d_hits_b[t0 * TILE:t1 * TILE], t0, t1, None)
+        gat_b.finish()
+        g1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device=tdev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        gather_ms = float(t.item())
+        # verification: rank 0's framebuffers hold every rank's records where ray order puts them
+        chk = torch.stack([d_hits_p[:, 0].long().sum(), d_hits_p[:, 1].long().sum(), d_hits_b[:, 0].long().sum(), d_hits_b[:, 1].long().sum()])
+        allc = [torch.zeros_like(chk) for _ in range(world)] if rank == 0 else None
+        dist.gather(chk, allc, 0)
+        if rank == 0:
+            for gat, base in ((gat_p, 0), (gat_b, 2)):
+                fb = gat.full.view(n_tiles, world, TILE, 6)
+                for rr in range(world):
+                    assert int(fb[:, rr, :, 0].long().sum()) == int(allc[rr][base]) and int(fb[:, rr, :, 1].long().sum()) == int(allc[rr][base + 1]), \
+                        f"gathered hit records of rank {rr} differ from what it traced"
+            assert torch.equal(gat_p.full.view(n_tiles, world, TILE, 6)[:, 0].reshape(-1, 6), d_hits_p)
     ms_per_step = total_ms / K
     value = world * 2 * n / (ms_per_step * 1e-3) / 1e6
 
@@ -404,17 +591,17 @@ def main():
         # the host path must return exactly what the resident path returned
         assert torch.equal(h_hits[:n], d_hits_p.cpu()) and torch.equal(h_hits[n:], d_hits_b.cpu())
 
-    # ------------------------------------------------------------------ gather the per-rank hit checksums (verification, untimed)
-    gather_ms = None
-    if world > 1:
-        chk = torch.stack([d_hits_p[:, 0].long().sum(), d_hits_b[:, 0].long().sum()])
-        out = [torch.zeros_like(chk) for _ in range(world)] if rank == 0 else None
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        dist.gather(chk, out, 0)
-        g1.record()
-        torch.cuda.synchronize()
-        gather_ms = g0.elapsed_time(g1)
+    # ------------------------------------------------------------------ BASELINE config 4, strong scaling (detail)
+    c4 = None
+    if not args.no_c4:
+        del gat_p, gat_b
+        torch.cuda.empty_cache()
+        try:
+            c4 = c4_strong(args, lc, dev, world, rank, barrier)
+        except torch.cuda.OutOfMemoryError as e:  # a smaller GPU than the 180 GB this is sized for
+            if world > 1:
+                raise
+            c4 = {"unavailable": f"out of memory: {e}"[:200]}
 
     if rank == 0:
         peaks = {}
@@ -439,6 +626,22 @@ def main():
                     "bytes_per_ray": float(bytes_b), "per_ray": {"nodes": float(cb[0]), "prims": float(cb[1]), "instances": float(cb[2])},
                     "roofline_mrays_s": peak * 1e9 / bytes_b / 1e6, "coherent": {"bytes_per_ray": float(bytes_p), "achieved": bytes_p * n / (tp_ms * 1e-3) / 1e9,
                                                                                  "per_ray": {"nodes": float(cp[0]), "prims": float(cp[1]), "instances": float(cp[2])}}}
+        # build roofline, SURVEY §8(d): bytes / primitive = 48 (3 vertices) + 12 (indices) + 2 * 8 * P (8-byte key read + written per
+        # radix pass; the primitive index rides in the key's low bits, there is no payload array) + 16 (bounds / centroid scratch)
+        # + 48 (triangle record out) + 80 * nodes / primitive (nodes out)
+        def build_roofline(n_prims, n_nodes, ms):
+            if not ms:
+                return None
+            lg = max(1, int(np.ceil(np.log2(max(n_prims, 2)))))
+            bits = min(max((int(np.ceil(np.log2(max(n_prims, 1)))) + 2) // 3 + 6, 10), 21, (64 - lg) // 3)
+            passes = (3 * bits + 7) // 8
+            bpp = 48 + 12 + 16 * passes + 16 + 48 + 80.0 * n_nodes / n_prims
+            ach = bpp * n_prims / (ms * 1e-3) / 1e9
+            return {"bound": "hbm", "bytes_per_prim": bpp, "radix_passes": passes, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "mprims_s": n_prims / ms / 1e3, "roofline_mprims_s": peak * 1e9 / bpp / 1e6, "ms": ms}
+        roofline_build = build_roofline(ntris, info.node_count, build_ms)
+        if c4 and c4.get("build_ms"):
+            c4["roofline_build"] = build_roofline(args.c4_tris, c4["bvh_nodes"], c4["build_ms"])
         cpu = None
         if not args.no_cpu_baseline:
             cpu = cpu_baseline(verts, tris, primary, bounce, args.cpu_sample)
@@ -453,14 +656,19 @@ def main():
                                    f"cosine-bounce closest-hit rays per GPU",
                        "l2_policy": f"inputs larger than L2: {2 * n * 32 / 1e6:.0f} MB rays + {2 * n * 24 / 1e6:.0f} MB hits + "
                                     f"{info.total_bytes / 1e6:.0f} MB BVH per step vs 126 MB L2",
-                       "sharding": "replicated scene, 65536-ray tiles round-robin over ranks, no collective in the timed region"},
+                       "sharding": ("single GPU" if world == 1 else f"replicated scene (BLAS built on rank 0, NCCL broadcast), 65536-ray tiles round-robin over {world} ranks; every "
+                                    f"rank's hit records are gathered into ray order on rank 0 INSIDE the timed region (NCCL send/recv per {CHUNK_TILES}-tile chunk "
+                                    f"on a side stream, overlapped with the next chunk's trace)")},
             "detail": {"coherent_closest_mrays_s": world * n / (tp_ms * 1e-3) / 1e6, "incoherent_closest_mrays_s": world * n / (tb_ms * 1e-3) / 1e6,
                        "incoherent_any_mrays_s": n / (any_ms * 1e-3) / 1e6, "primary_hit_fraction": hit_frac_p,
                        "blas_build_ms": build_ms, "blas_build_mtris_s": (ntris / (build_ms * 1e-3) / 1e6) if build_ms else None,
                        "numa_binding": list(numa) if numa else None, "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
+                       "hit_gather_note": None if world == 1 else f"one batch ({(world - 1) * n * 24 / 1e6:.0f} MB into rank 0) gathered alone, nothing to overlap with; in the step it hides behind the traces",
+                       "c4_strong": c4,
                        "scene_gen_s": gen_s},
-            "roofline": roofline, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin_backend": dropin, "e2e": e2e, "clocks": clocks,
-            "gpu_launches": 4 * K,  # per step: k_trace + k_refine_hits for the primary batch and for the bounce batch
+            "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin_backend": dropin, "e2e": e2e, "clocks": clocks,
+            # per step: k_trace + k_refine_hits per launch; one launch per batch at N = 1, one per CHUNK_TILES tiles otherwise
+            "gpu_launches": 4 * K if world == 1 else 4 * K * ((n_tiles + CHUNK_TILES - 1) // CHUNK_TILES),
         }
         print(json.dumps(line))
     if world > 1:

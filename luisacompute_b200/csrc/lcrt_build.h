@@ -197,8 +197,18 @@ LCRT_HD uint64_t morton63(const Box &b, const float clo[3], const float inv_ext[
     return code;
 }
 
-// Bits per axis: enough to resolve 64 cells per primitive (per axis) of a uniform distribution, at most 21.  The number
-// of 8-bit radix passes follows: ceil(3 * bits / 8) — 5 passes up to 2 M primitives, 6 up to 128 M.
+// Sort key = (Morton code << index_bits) | primitive index: ONE 64-bit word per primitive goes through the radix sort (no
+// payload array), keys are unique by construction (duplicate Morton codes split by index, which is what the LBVH tie-break
+// did explicitly before) and the sorted order IS the key's low bits.  Only the Morton bits are sorted: the keys start in
+// index order and the sort is stable.
+LCRT_HD uint32_t index_bits_for(uint32_t n) {
+    uint32_t lg = 1;
+    while ((1ull << lg) < (uint64_t)n) lg++;
+    return lg;
+}
+// Morton bits per axis: enough to resolve 64 cells per primitive (per axis) of a uniform distribution, at most 21 and at
+// most what the key has room for next to the index.  The number of 8-bit radix passes follows: ceil(3 * bits / 8) —
+// 5 passes at 1.3 M primitives (13 bits per axis), 5 at 50 M (12 bits per axis).
 #ifndef LCRT_MORTON_EXTRA_BITS
 #define LCRT_MORTON_EXTRA_BITS 6u
 #endif
@@ -208,78 +218,97 @@ LCRT_HD uint32_t morton_bits_for(uint32_t n) {
     uint32_t b = (lg + 2u) / 3u + LCRT_MORTON_EXTRA_BITS;
     if (b < 10u) b = 10u;
     if (b > 21u) b = 21u;
+    const uint32_t room = (64u - index_bits_for(n)) / 3u;
+    if (b > room) b = room;
     return b;
 }
 
 // ------------------------------------------------------------------------------------------ binary hierarchy
-// Node ids: internal j in [0, n-1), leaf i -> (n-1) + i.  Boxes for all 2n-1 nodes in lo/hi (xyz), with
-//   lo.w = SAH cost of the subtree, hi.w = bits(count | LEAF_MARK if the subtree is collapsed into one leaf slot)
+// Node ids: internal j in [0, n-1), leaf i -> (n-1) + i.  Everything known about a node lives in its PARENT's record, one
+// 48-byte half per child: opening a child during the collapse is ONE dependent load (both grandchildren with their
+// boxes, leaf marks, leaf-slot counts and ranges arrive together), and a leaf-marked subtree's primitives are the
+// sorted positions first .. first + count - 1, so nothing below it is ever traversed.
+struct alignas(16) Bvh2Half {
+    float lo[3];
+    float cost;          // SAH cost of the subtree
+    float hi[3];
+    uint32_t count_mark; // primitives below | LEAF_MARK if the subtree is collapsed into one leaf slot
+    uint32_t id;         // node id of this child
+    uint32_t slots;      // leaf slots below it (1 for a leaf-marked subtree)
+    uint32_t first, last;// range of sorted positions below it
+};
+static_assert(sizeof(Bvh2Half) == 48, "Bvh2Half must be 48 bytes");
+struct alignas(16) Bvh2Node {
+    Bvh2Half l, r;
+};
+static_assert(sizeof(Bvh2Node) == 96, "Bvh2Node must be 96 bytes");
+
 struct Bvh2 {
     uint32_t n;
-    const uint64_t *keys;  // sorted Morton codes
-    const uint32_t *order; // sorted position -> input primitive
-    f4 *lo, *hi;           // [2n-1]
-    u2 *child;             // [n-1]
-    u2 *range;             // [n-1]  (left end set by the left child, right end by the right child)
-    uint32_t *flag;        // [n-1]  zero-initialised arrival counters; once a node is complete: its number of leaf slots
-    uint32_t *root;        // [1]
+    uint32_t index_bits;   // low bits of a key = input primitive
+    const uint64_t *keys;  // sorted keys
+    Bvh2Node *node;        // [n-1]
+    uint32_t *flag;        // [n-1]  zero-initialised arrival counters
+    Bvh2Half *root;        // [1]    the root described like a child
     float ci;              // cost of one binary split relative to one primitive test
     uint32_t max_leaf;
+    LCRT_HD uint32_t order(uint32_t pos) const { return (uint32_t)(keys[pos] & ((1ull << index_bits) - 1ull)); }
 };
 
 LCRT_HD bool delta_less(const uint64_t *keys, uint32_t a, uint32_t b) {// delta(a) < delta(b); delta(j) between j and j+1
-    const uint64_t xa = keys[a] ^ keys[a + 1], xb = keys[b] ^ keys[b + 1];
-    if (xa != xb) return xa < xb;
-    return (a ^ (a + 1)) < (b ^ (b + 1));
+    const uint64_t xa = keys[a] ^ keys[a + 1], xb = keys[b] ^ keys[b + 1];// keys are unique: no tie-break needed
+    return xa < xb;
 }
 
-LCRT_HD float area_of(const f4 lo, const f4 hi) {
-    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+LCRT_HD float area_of(const float *lo, const float *hi) {
+    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
     if (!(dx >= 0.f) || !(dy >= 0.f) || !(dz >= 0.f)) return 0.f;
     return dx * dy + dy * dz + dz * dx;
+}
+
+LCRT_HD void store_half(Bvh2Half *dst, const Bvh2Half &h) { copy_vec16(dst, &h, 3); }
+LCRT_HD Bvh2Half load_half_cg(const Bvh2Half *src) {// written by another SM inside the same kernel: not from this SM's L1
+    Bvh2Half h;
+#if defined(__CUDA_ARCH__)
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    float4 *d = reinterpret_cast<float4 *>(&h);
+    d[0] = __ldcg(s), d[1] = __ldcg(s + 1), d[2] = __ldcg(s + 2);
+#else
+    h = *src;
+#endif
+    return h;
 }
 
 // one thread per leaf (Apetrei 2014): climbs while it is the second child to arrive
 LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
     const uint32_t n = t.n;
-    uint32_t left = i, right = i, cur = (n - 1) + i;
-    f4 lo = make_f4(leaf_box.lo[0], leaf_box.lo[1], leaf_box.lo[2], 0.f);
-    f4 hi = make_f4(leaf_box.hi[0], leaf_box.hi[1], leaf_box.hi[2], 0.f);
-    float cost = area_of(lo, hi);
-    uint32_t count = 1u, mark = LEAF_MARK, slots = 1u;
+    uint32_t left = i, right = i;
+    Bvh2Half h;
+    for (int a = 0; a < 3; a++) h.lo[a] = leaf_box.lo[a], h.hi[a] = leaf_box.hi[a];
+    h.cost = area_of(h.lo, h.hi), h.count_mark = 1u | LEAF_MARK, h.id = (n - 1u) + i, h.slots = 1u, h.first = i, h.last = i;
     for (;;) {
-        lo.w = cost, hi.w = as_float(count | mark);
-        t.lo[cur] = lo, t.hi[cur] = hi;
-        if (cur < n - 1u) t.flag[cur] = slots;// the arrival counter has done its job
         if (left == 0u && right == n - 1u) {
-            *t.root = cur;
+            store_half(t.root, h);
             return;
         }
         uint32_t parent;
         bool from_left;
-        if (left == 0u || (right != n - 1u && delta_less(t.keys, right, left - 1u))) {
-            parent = right, from_left = true;
-            t.child[parent].x = cur, t.range[parent].x = left;
-        } else {
-            parent = left - 1u, from_left = false;
-            t.child[parent].y = cur, t.range[parent].y = right;
-        }
+        if (left == 0u || (right != n - 1u && delta_less(t.keys, right, left - 1u))) parent = right, from_left = true;
+        else parent = left - 1u, from_left = false;
+        store_half(from_left ? &t.node[parent].l : &t.node[parent].r, h);
         if (LCRT_ATOMIC_ADD_ACQ_REL(&t.flag[parent], 1u) == 0u) return;// the sibling will finish this node
         // second arrival: merge with the sibling
-        const uint32_t sib = LCRT_VOLATILE_LOAD_U32(from_left ? &t.child[parent].y : &t.child[parent].x);
-        if (from_left) right = LCRT_VOLATILE_LOAD_U32(&t.range[parent].y);
-        else left = LCRT_VOLATILE_LOAD_U32(&t.range[parent].x);
-        const f4 slo = LCRT_LOAD_CG_F4(&t.lo[sib]), shi = LCRT_LOAD_CG_F4(&t.hi[sib]);
-        lo.x = fminf(lo.x, slo.x), lo.y = fminf(lo.y, slo.y), lo.z = fminf(lo.z, slo.z);
-        hi.x = fmaxf(hi.x, shi.x), hi.y = fmaxf(hi.y, shi.y), hi.z = fmaxf(hi.z, shi.z);
-        count += as_uint(shi.w) & ~LEAF_MARK;
-        slots += sib < n - 1u ? LCRT_VOLATILE_LOAD_U32(&t.flag[sib]) : 1u;
-        const float area = area_of(lo, hi);
-        const float c_split = t.ci * area + cost + slo.w;
+        const Bvh2Half s = load_half_cg(from_left ? &t.node[parent].r : &t.node[parent].l);
+        if (from_left) right = s.last;
+        else left = s.first;
+        for (int a = 0; a < 3; a++) h.lo[a] = fminf(h.lo[a], s.lo[a]), h.hi[a] = fmaxf(h.hi[a], s.hi[a]);
+        const uint32_t count = (h.count_mark & ~LEAF_MARK) + (s.count_mark & ~LEAF_MARK);
+        const float area = area_of(h.lo, h.hi);
+        const float c_split = t.ci * area + h.cost + s.cost;
         const float c_leaf = area * (float)count;
-        if (count <= t.max_leaf && c_leaf <= c_split) cost = c_leaf, mark = LEAF_MARK, slots = 1u;
-        else cost = c_split, mark = 0u;
-        cur = parent;
+        if (count <= t.max_leaf && c_leaf <= c_split) h.cost = c_leaf, h.count_mark = count | LEAF_MARK, h.slots = 1u;
+        else h.cost = c_split, h.count_mark = count, h.slots = h.slots + s.slots;
+        h.id = parent, h.first = left, h.last = right;
     }
 }
 
@@ -289,12 +318,13 @@ struct Bvh8Out {
     Node8 *nodes;
     char *prims;
     uint32_t *parent;     // optional (allow_update): (parent << 3) | slot
-    uint32_t *task;       // [node_capacity] bvh2 node id per wide node, INVALID until scheduled
+    u2 *task;             // [node_capacity] { binary node id, depth of the wide node } per wide node, x == INVALID until scheduled
     uint32_t *rec_src;    // [prim_count] sorted position whose primitive goes into record j (records are written by a
                           // separate, fully parallel pass: emit_record)
-    uint32_t *counters;   // [0] nodes allocated, [1] prims allocated, [2] prims finished
+    uint32_t *counters;   // nodes allocated, prims allocated, prims finished — at [0], [COUNTER_STRIDE], [2 * COUNTER_STRIDE]
     uint32_t node_capacity;
 };
+constexpr uint32_t COUNTER_STRIDE = 32;// words: every counter on its own 128-byte line
 
 // Quantisation of child boxes onto the node's 8-bit grid: origin p = node lo, per-axis step 2^(e-127) with e the
 // smallest exponent for which 255 steps span the node, child lo rounded down and hi rounded up.  The host evaluates
@@ -364,93 +394,96 @@ LCRT_HD void quantize_node(Node8 &nd, const Box &nb, const Box *cb, const bool *
     }
 }
 
-// collect the sorted positions of the primitives under a leaf-marked subtree (count <= 3)
-LCRT_HD uint32_t gather_leaf(const Bvh2 &t, uint32_t id, uint32_t *out, uint32_t cap) {
-    uint32_t stack[8];
-    int sp = 0;
-    uint32_t k = 0;
-    stack[sp++] = id;
-    while (sp) {
-        const uint32_t c = stack[--sp];
-        if (c >= t.n - 1u) {
-            if (k < cap) out[k++] = c - (t.n - 1u);
-        } else {
-            const u2 ch = t.child[c];
-            stack[sp++] = ch.y, stack[sp++] = ch.x;
-        }
-    }
-    return k;
-}
-
-// Builds wide node `widx` from binary subtree `bid`.  Returns false on capacity overflow.
+// Builds wide node `widx` (at depth `depth`, root = 1) from the binary node `bid`; for widx == 0 the root comes described as
+// a half (Bvh2::root).  Returns false on capacity overflow.  This is the serial statement of the algorithm (tests/hostsim
+// runs it); the device runs the same decisions with eight lanes per node (collapse_octet, lcrt_kernels.cu).
 template<class Input>
-LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid) {
-    uint32_t cid[8];
-    Box cbox[8];
+LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid, uint32_t depth) {
+    Bvh2Half c[8];
     float carea[8];
     bool cleaf[8];
     int nc = 0;
-    auto load_child = [&](int k, uint32_t id) {
-        const f4 lo = t.lo[id], hi = t.hi[id];
-        cid[k] = id;
-        cbox[k].lo[0] = lo.x, cbox[k].lo[1] = lo.y, cbox[k].lo[2] = lo.z;
-        cbox[k].hi[0] = hi.x, cbox[k].hi[1] = hi.y, cbox[k].hi[2] = hi.z;
-        carea[k] = area_of(lo, hi);
-        cleaf[k] = (as_uint(hi.w) & LEAF_MARK) != 0u;
+    auto set_child = [&](int k, const Bvh2Half &h) {
+        c[k] = h;
+        carea[k] = area_of(h.lo, h.hi);
+        cleaf[k] = (h.count_mark & LEAF_MARK) != 0u;
     };
-    {
-        const f4 hi = t.hi[bid];
-        if (as_uint(hi.w) & LEAF_MARK) {
-            load_child(0, bid);
-            nc = 1;
+    if (widx == 0u) {
+        const Bvh2Half r = *t.root;
+        if (r.count_mark & LEAF_MARK) {
+            set_child(0, r), nc = 1;
         } else {
-            const u2 ch = t.child[bid];
-            load_child(0, ch.x), load_child(1, ch.y);
-            nc = 2;
+            bid = r.id;
         }
     }
+    if (nc == 0) {
+        const Bvh2Node nd = t.node[bid];
+        set_child(0, nd.l), set_child(1, nd.r), nc = 2;
+    }
     // Opening policy.  Every wide node below the top levels should be as full as possible, so the binary subtree is
-    // opened by leaf-slot counts (lbvh_climb leaves them in flag[]):
+    // opened by leaf-slot counts (lbvh_climb leaves them in the halves):
     //   * a subtree of <= 8 leaf slots becomes ONE wide node whose children are all leaves;
     //   * otherwise children with more than 8 leaf slots are opened first, largest surface area first (the classic
     //     greedy rule, which is what the upper levels see);
     //   * then, smallest first, children small enough to be dissolved into leaf slots of this node entirely are
     //     dissolved; what is left (<= 8 leaf slots each) becomes full-ish all-leaf nodes one level down.
-    auto slots_of = [&](uint32_t id) -> uint32_t { return id < t.n - 1u ? t.flag[id] : 1u; };
-    uint32_t cslots[8];
-    for (int k = 0; k < nc; k++) cslots[k] = cleaf[k] ? 1u : slots_of(cid[k]);
     auto open_child = [&](int k) {
-        const u2 ch = t.child[cid[k]];
-        load_child(k, ch.x), cslots[k] = cleaf[k] ? 1u : slots_of(ch.x);
-        load_child(nc, ch.y), cslots[nc] = cleaf[nc] ? 1u : slots_of(ch.y);
+        const Bvh2Node nd = t.node[c[k].id];
+        set_child(k, nd.l), set_child(nc, nd.r);
         nc++;
     };
-    while (nc < 8) {
-        int best = -1;
-        float ba = -1.f;
-        for (int k = 0; k < nc; k++)
-            if (!cleaf[k] && cslots[k] > 8u && carea[k] > ba) ba = carea[k], best = k;
-        if (best < 0) break;
-        open_child(best);
-    }
-    for (;;) {
-        int best = -1;
-        uint32_t bs = 0xffffffffu;
-        for (int k = 0; k < nc; k++)
-            if (!cleaf[k] && (uint32_t)nc - 1u + cslots[k] <= 8u && cslots[k] < bs) bs = cslots[k], best = k;
-        if (best < 0) break;
-        // dissolve the whole subtree of that child: every opening yields pieces that still fit
-        uint32_t pending = 1u << best;
-        while (pending) {
-            const int k = bfind(pending);
-            pending &= ~(1u << k);
-            if (cleaf[k]) continue;
-            open_child(k);
-            pending |= (1u << k) | (1u << (nc - 1));
+    uint32_t total_slots = 0;
+    for (int k = 0; k < nc; k++) total_slots += c[k].slots;
+    if (total_slots <= 8u) {
+        // the whole subtree fits into this node (six wide nodes out of seven are of this kind): dissolve it level by level,
+        // every internal child of a round at once — left halves stay in place, right halves are appended in child order
+        for (;;) {
+            uint32_t opening = 0u;
+            for (int k = 0; k < nc; k++)
+                if (!cleaf[k]) opening |= 1u << k;
+            if (!opening) break;
+            const int base = nc;
+            int rank = 0;
+            for (int k = 0; k < base; k++) {
+                if (!(opening & (1u << k))) continue;
+                const Bvh2Node nd = t.node[c[k].id];
+                set_child(k, nd.l), set_child(base + rank, nd.r);
+                rank++;
+            }
+            nc = base + rank;
+        }
+    } else {
+        while (nc < 8) {
+            int best = -1;
+            float ba = -1.f;
+            for (int k = 0; k < nc; k++)
+                if (!cleaf[k] && c[k].slots > 8u && carea[k] > ba) ba = carea[k], best = k;
+            if (best < 0) break;
+            open_child(best);
+        }
+        for (;;) {
+            int best = -1;
+            uint32_t bs = 0xffffffffu;
+            for (int k = 0; k < nc; k++)
+                if (!cleaf[k] && (uint32_t)nc - 1u + c[k].slots <= 8u && c[k].slots < bs) bs = c[k].slots, best = k;
+            if (best < 0) break;
+            // dissolve the whole subtree of that child: every opening yields pieces that still fit
+            uint32_t pending = 1u << best;
+            while (pending) {
+                const int k = bfind(pending);
+                pending &= ~(1u << k);
+                if (cleaf[k]) continue;
+                open_child(k);
+                pending |= (1u << k) | (1u << (nc - 1));
+            }
         }
     }
+    Box cbox[8];
     Box nb = box_empty();
-    for (int k = 0; k < nc; k++) box_grow(nb, cbox[k]);
+    for (int k = 0; k < nc; k++) {
+        for (int a = 0; a < 3; a++) cbox[k].lo[a] = c[k].lo[a], cbox[k].hi[a] = c[k].hi[a];
+        box_grow(nb, cbox[k]);
+    }
     // ---- octant-ordered slot assignment (greedy maximum of (centroid - centre) . octant sign)
     float cx = 0.5f * (nb.lo[0] + nb.hi[0]), cy = 0.5f * (nb.lo[1] + nb.hi[1]), cz = 0.5f * (nb.lo[2] + nb.hi[2]);
     if (!(cx == cx)) cx = 0.f;
@@ -479,11 +512,11 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
     // ---- allocate children / primitive records
     uint32_t n_int = 0, n_prims = 0;
     for (int k = 0; k < nc; k++) {
-        if (cleaf[k]) n_prims += as_uint(t.hi[cid[k]].w) & ~LEAF_MARK;
+        if (cleaf[k]) n_prims += c[k].count_mark & ~LEAF_MARK;
         else n_int++;
     }
-    const uint32_t child_base = n_int ? LCRT_ATOMIC_ADD(&o.counters[0], n_int) : 0u;
-    const uint32_t prim_base = n_prims ? LCRT_ATOMIC_ADD(&o.counters[1], n_prims) : 0u;
+    const uint32_t child_base = n_int ? LCRT_ATOMIC_ADD(&o.counters[0 * COUNTER_STRIDE], n_int) : 0u;
+    const uint32_t prim_base = n_prims ? LCRT_ATOMIC_ADD(&o.counters[1 * COUNTER_STRIDE], n_prims) : 0u;
     if (n_int && child_base + n_int > o.node_capacity) {
         o.header->error = 1u;
         return false;
@@ -505,11 +538,11 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
             nd.imask |= (uint8_t)(1u << s);
             nd.meta[s] = (uint8_t)((1u << 5) | (24u + (uint32_t)s));
             if (o.parent) o.parent[w] = (widx << 3) | (uint32_t)s;
-            o.task[w] = cid[k];
+            o.task[w] = make_u2(c[k].id, depth + 1u);
         } else {
-            uint32_t pos[4];
-            const uint32_t cnt = gather_leaf(t, cid[k], pos, 3u);
-            for (uint32_t q = 0; q < cnt; q++) o.rec_src[prim_base + po + q] = pos[q];
+            // a leaf slot holds the primitives at the sorted positions first .. first + count - 1 of its subtree
+            const uint32_t cnt = c[k].count_mark & ~LEAF_MARK;
+            for (uint32_t q = 0; q < cnt; q++) o.rec_src[prim_base + po + q] = c[k].first + q;
             const uint32_t unary = cnt == 1u ? 1u : cnt == 2u ? 3u : 7u;
             nd.meta[s] = (uint8_t)((unary << 5) | po);
             po += cnt;
@@ -522,7 +555,7 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
         if (o.parent) o.parent[0] = INVALID_U32;
     }
     // tasks and parents are released before the completion counter moves
-    if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2], n_prims);
+    if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], n_prims);
     else LCRT_FENCE();
     return true;
 }
@@ -530,7 +563,7 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
 // record j of the blob <- primitive order[rec_src[j]] (one thread per record)
 template<class Input>
 LCRT_HD void emit_record(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t j) {
-    in.write(o.prims + (uint64_t)j * Input::rec_bytes, t.order[o.rec_src[j]]);
+    in.write(o.prims + (uint64_t)j * Input::rec_bytes, t.order(o.rec_src[j]));
 }
 
 // ------------------------------------------------------------------------------------------ refit

@@ -25,16 +25,24 @@
 
 namespace lcrt {
 
-static_assert(SORT_TILE == SORT_TILE_KEYS, "lcrt_layout.h and lcrt_sort.cuh disagree on the sort tile");
+static_assert(SORT_TILE == SORT_TILE_KEYS && SORT_CONTROL_PASSES == SORT_MAX_PASSES, "lcrt_layout.h and lcrt_sort.cuh disagree on the sort tile");
 
 // =====================================================================================================================
 // build kernels
 // =====================================================================================================================
-enum SmallSlots : uint32_t { SM_CMIN = 0, SM_CMAX = 3, SM_ROOT = 6, SM_ABORT = 7, SM_COUNTERS = 8 /* nodes, prims, done */, SM_BARRIER = 11 /* arrivals, generation, node-count snapshots [2] */,
-                           SM_LEVELS = 15 /* BVH8 levels the collapse processed */, SM_CHILD_DEPTH = 16 /* TLAS: deepest instanced BLAS */ };
-static_assert(SM_CHILD_DEPTH < SMALL_WORDS, "scratch words");
+enum SmallSlots : uint32_t {
+    SM_CMIN = 0, SM_CMAX = 3, SM_LEVELS = 15 /* depth of the wide hierarchy */, SM_CHILD_DEPTH = 16 /* TLAS: deepest instanced BLAS */,
+    SM_ROOT_HALF = 32 /* Bvh2Half of the root (12 words, 16-byte aligned) */,
+    // the words every wide node touches, each on its own 128-byte line (they are served by one L2 slice each; sharing a
+    // line with the polled flags made the counters' atomics queue behind the polls)
+    SM_COUNTERS = 64 /* nodes, prims, done prims at COUNTER_STRIDE words */, SM_DONE = 160 /* every primitive has its record slot */, SM_ABORT = 192
+};
+static_assert(SM_COUNTERS + 2 * COUNTER_STRIDE < SM_DONE && SM_ABORT < SMALL_WORDS, "scratch words");
+static_assert(SM_ROOT_HALF * 4 % 16 == 0 && SM_ROOT_HALF + sizeof(Bvh2Half) / 4 <= SMALL_WORDS, "scratch words");
 
 __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t flags, BlobLayout L, uint32_t *small) {
+    for (uint32_t k = threadIdx.x; k < SMALL_WORDS; k += blockDim.x) small[k] = 0u;
+    __syncthreads();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         BlobHeader hd;
         memset(&hd, 0, sizeof(hd));
@@ -45,11 +53,7 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
         for (int a = 0; a < 3; a++) hd.lo[a] = INFINITY, hd.hi[a] = -INFINITY;
         *h = hd;
         small[SM_CMIN + 0] = small[SM_CMIN + 1] = small[SM_CMIN + 2] = 0xffffffffu;
-        small[SM_CMAX + 0] = small[SM_CMAX + 1] = small[SM_CMAX + 2] = 0u;
-        small[SM_ROOT] = INVALID_U32, small[SM_ABORT] = 0u;
-        small[SM_COUNTERS + 0] = 1u, small[SM_COUNTERS + 1] = 0u, small[SM_COUNTERS + 2] = 0u;
-        small[SM_BARRIER + 0] = small[SM_BARRIER + 1] = small[SM_BARRIER + 2] = small[SM_BARRIER + 3] = 0u;
-        small[SM_LEVELS] = 0u, small[SM_CHILD_DEPTH] = 0u;
+        small[SM_COUNTERS + 0 * COUNTER_STRIDE] = 1u;// the root
         if (n == 0u) {
             // an empty structure: one node with no children; nothing can be hit
             Node8 nd;
@@ -67,11 +71,15 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
     }
 }
 
+// primitive boxes (kept, in input order: the Morton pass streams them, the climb gathers 32 bytes per leaf instead of
+// re-fetching indices and vertices) and the bounds of their centres
 template<class Input>
-__global__ void __launch_bounds__(256) k_centroid_bounds(Input in, uint32_t *small) {
+__global__ void __launch_bounds__(256) k_prim_bounds(Input in, f4 *__restrict__ pbox, uint32_t *small) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+#pragma unroll 2
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < in.n; i += gridDim.x * blockDim.x) {
         const Box b = in.box(i);
+        pbox[2ull * i] = make_f4(b.lo[0], b.lo[1], b.lo[2], 0.f), pbox[2ull * i + 1] = make_f4(b.hi[0], b.hi[1], b.hi[2], 0.f);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
             const float c = 0.5f * (b.lo[a] + b.hi[a]);
@@ -86,7 +94,7 @@ __global__ void __launch_bounds__(256) k_centroid_bounds(Input in, uint32_t *sma
             hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
         }
     }
-    // one set of atomics per block (the six words are a hot spot: per-warp atomics cost a third of this kernel's time)
+    // one set of atomics per block (the six words are a hot spot)
     __shared__ float s_lo[3][8], s_hi[3][8];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     if (lane == 0u) {
@@ -106,9 +114,14 @@ __global__ void __launch_bounds__(256) k_centroid_bounds(Input in, uint32_t *sma
     }
 }
 
-template<class Input>
-__global__ void __launch_bounds__(256) k_morton(Input in, const uint32_t *__restrict__ small, uint64_t *__restrict__ keys,
-                                                uint32_t *__restrict__ vals, uint32_t bits) {
+LCRT_HD Box box_from_pbox(const f4 lo, const f4 hi) {
+    Box b;
+    b.lo[0] = lo.x, b.lo[1] = lo.y, b.lo[2] = lo.z, b.hi[0] = hi.x, b.hi[1] = hi.y, b.hi[2] = hi.z;
+    return b;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const f4 *__restrict__ pbox, uint32_t n, const uint32_t *__restrict__ small, uint64_t *__restrict__ keys,
+                                                uint32_t bits, uint32_t index_bits) {
     float clo[3], inv_ext[3];
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -119,107 +132,118 @@ __global__ void __launch_bounds__(256) k_morton(Input in, const uint32_t *__rest
         if (ulo == 0xffffffffu) clo[a] = 0.f, inv_ext[a] = 0.f;
     }
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < in.n) {
-        keys[i] = morton63(in.box(i), clo, inv_ext, bits);
-        vals[i] = i;
+    if (i < n) keys[i] = (morton63(box_from_pbox(pbox[2ull * i], pbox[2ull * i + 1]), clo, inv_ext, bits) << index_bits) | (uint64_t)i;
+}
+
+__global__ void __launch_bounds__(64) k_climb(Bvh2 t, const f4 *__restrict__ pbox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < t.n) {
+        const uint32_t p = t.order(i);
+        lbvh_climb(t, i, box_from_pbox(pbox[2ull * p], pbox[2ull * p + 1]));
     }
 }
 
-template<class Input>
-__global__ void __launch_bounds__(256) k_climb(Bvh2 t, Input in) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < t.n) lbvh_climb(t, i, in.box(t.order[i]));
-}
-
 #ifndef LCRT_COLLAPSE_MIN_BLOCKS
-#define LCRT_COLLAPSE_MIN_BLOCKS 4
+#define LCRT_COLLAPSE_MIN_BLOCKS 6
 #endif
 constexpr int COLLAPSE_BLOCK = 128;
-#ifndef LCRT_COLLAPSE_OCTET_WAVES
-#define LCRT_COLLAPSE_OCTET_WAVES 4   // levels of up to this many grid-loads of octets use the eight-lanes-per-node path
-#endif
 
 // ---- collapse_node() (lcrt_build.h, the serial statement the host simulation runs) done by EIGHT lanes per wide node:
-// lane k of an "octet" owns child k (binary node id, box, area, leaf mark, leaf-slot count) in registers, so nothing
-// is indexed dynamically in local memory; the choices (which child to open, which (child, slot) pair to assign next)
-// are arg-max reductions over the octet with three __shfl_xor steps, and the per-child work (leaf gathering,
-// quantisation) runs in parallel.  Every decision is the serial one (same tie-breaks), so both produce the same tree.
-// All shuffles are executed by the full warp: control flow is warp-uniform, per-octet activity is a predicate.
+// lane k of an "octet" owns child k (its Bvh2Half) in registers, so nothing is indexed dynamically in local memory; the
+// choices (which child to open, which (child, slot) pair to assign next) are arg-max reductions over the octet with three
+// __shfl_xor steps, and the per-child work (leaf records, quantisation) runs in parallel.  Opening a child is ONE
+// dependent load: the binary node record carries both grandchildren completely.  Every decision is the serial one
+// (same tie-breaks), so both produce the same tree.  All shuffles are executed by the full warp: control flow is
+// warp-uniform, per-octet activity is a predicate.
 struct OctChild {
     uint32_t id;
     float lox, loy, loz, hix, hiy, hiz, area;
     bool valid, leaf;
-    uint32_t slots, count;// leaf slots below the child; primitives in it if it is a leaf
+    uint32_t slots, count, first;// leaf slots below the child; primitives in it and their first sorted position if it is a leaf
 };
-__device__ __forceinline__ void oct_load(const Bvh2 &t, OctChild &c, uint32_t id) {
-    const f4 lo = t.lo[id], hi = t.hi[id];
-    c.id = id, c.valid = true;
-    c.lox = lo.x, c.loy = lo.y, c.loz = lo.z, c.hix = hi.x, c.hiy = hi.y, c.hiz = hi.z;
-    c.area = area_of(lo, hi);
-    c.leaf = (as_uint(hi.w) & LEAF_MARK) != 0u;
-    c.count = as_uint(hi.w) & ~LEAF_MARK;
-    c.slots = c.leaf ? 1u : (id < t.n - 1u ? t.flag[id] : 1u);
+__device__ __forceinline__ void oct_set(OctChild &c, const Bvh2Half *src) {
+    const float4 *s = reinterpret_cast<const float4 *>(src);
+    const float4 a = __ldg(s), b = __ldg(s + 1);
+    const uint4 m = __ldg(reinterpret_cast<const uint4 *>(s + 2));
+    c.valid = true;
+    c.lox = a.x, c.loy = a.y, c.loz = a.z, c.hix = b.x, c.hiy = b.y, c.hiz = b.z;
+    const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
+    c.area = (!(dx >= 0.f) || !(dy >= 0.f) || !(dz >= 0.f)) ? 0.f : dx * dy + dy * dz + dz * dx;// area_of
+    const uint32_t cm = __float_as_uint(b.w);
+    c.leaf = (cm & LEAF_MARK) != 0u;
+    c.count = cm & ~LEAF_MARK;
+    c.id = m.x, c.slots = m.y, c.first = m.z;
 }
 // opens child `k` of every octet with `go`: its left child stays in lane k, its right child goes to lane nc
 __device__ __forceinline__ void oct_open(const Bvh2 &t, OctChild &c, uint32_t l, bool go, uint32_t k, uint32_t &nc) {
-    u2 ch = make_u2(0u, 0u);
-    if (go && l == k) ch = t.child[c.id];
-    ch.x = __shfl_sync(0xffffffffu, ch.x, (int)k, 8), ch.y = __shfl_sync(0xffffffffu, ch.y, (int)k, 8);
-    if (go && l == k) oct_load(t, c, ch.x);
-    if (go && l == nc) oct_load(t, c, ch.y);
+    const uint32_t id = __shfl_sync(0xffffffffu, c.id, (int)k, 8);
+    if (go && l == k) oct_set(c, &t.node[id].l);
+    if (go && l == nc) oct_set(c, &t.node[id].r);
     if (go) nc++;
 }
-// arg-max of `key` over the octet among lanes with `cand`; ties go to the lower lane; returns 8 if there is no candidate
-__device__ __forceinline__ uint32_t oct_argmax(float key, bool cand, uint32_t l) {
-    uint32_t who = cand ? l : 8u;
-#pragma unroll
-    for (int m = 1; m < 8; m <<= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, key, m, 8);
-        const uint32_t ow = __shfl_xor_sync(0xffffffffu, who, m, 8);
-        const bool take = ow < 8u && (who == 8u || ok > key || (ok == key && ow < who));
-        if (take) key = ok, who = ow;
-    }
-    return who;
+// arg-max over the octet of an integer key (0 = "not a candidate"); ties go to the lower lane; returns 8 if there is no
+// candidate.  Two REDUX instructions on the octet's own lane mask instead of a three-step shuffle tree.
+__device__ __forceinline__ uint32_t oct_argmax(uint32_t key, uint32_t l, uint32_t omask) {
+    const uint32_t m = __reduce_max_sync(omask, key);
+    return __reduce_min_sync(omask, (key == m && m != 0u) ? l : 8u);
 }
-__device__ __forceinline__ uint32_t oct_or(uint32_t v) {
-#pragma unroll
-    for (int m = 1; m < 8; m <<= 1) v |= __shfl_xor_sync(0xffffffffu, v, m, 8);
-    return v;
-}
+__device__ __forceinline__ uint32_t oct_or(uint32_t v, uint32_t omask) { return __reduce_or_sync(omask, v); }
 
 template<class Input>
-__device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid, bool act, unsigned char *node_smem) {
+__device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid, uint32_t depth, bool act,
+                               unsigned char *node_smem, uint32_t *done_flag) {
     const uint32_t l = threadIdx.x & 7u;
     OctChild c;
-    c.id = INVALID_U32, c.valid = false, c.leaf = true, c.slots = 0u, c.count = 0u, c.area = 0.f;
+    c.id = INVALID_U32, c.valid = false, c.leaf = true, c.slots = 0u, c.count = 0u, c.first = 0u, c.area = 0.f;
     c.lox = c.loy = c.loz = INFINITY, c.hix = c.hiy = c.hiz = -INFINITY;
     uint32_t nc = 0u;
-    if (act) {
-        const f4 hi = t.hi[bid];
-        if (as_uint(hi.w) & LEAF_MARK) {
+    if (act && widx == 0u) {
+        // the root arrives described as a half: a leaf-marked root (<= 3 primitives in all) is the node's only child
+        const uint32_t cm = t.root->count_mark;
+        if (cm & LEAF_MARK) {
             nc = 1u;
-            if (l == 0u) oct_load(t, c, bid);
+            if (l == 0u) oct_set(c, t.root);
         } else {
-            const u2 ch = t.child[bid];
-            nc = 2u;
-            if (l == 0u) oct_load(t, c, ch.x);
-            if (l == 1u) oct_load(t, c, ch.y);
+            bid = t.root->id;
         }
     }
-    // ---- open the largest child with more than 8 leaf slots until the node is full
-    for (;;) {
-        const bool cand = act && nc < 8u && c.valid && !c.leaf && c.slots > 8u;
-        const uint32_t best = oct_argmax(c.area, cand, l);
-        if (!__any_sync(0xffffffffu, best < 8u)) break;
-        oct_open(t, c, l, best < 8u, best & 7u, nc);
+    if (act && nc == 0u) {
+        nc = 2u;
+        if (l == 0u) oct_set(c, &t.node[bid].l);
+        if (l == 1u) oct_set(c, &t.node[bid].r);
     }
-    // ---- dissolve, smallest first, children whose whole subtree fits into the free slots
-    {
+    const uint32_t omask = 0xffu << (threadIdx.x & 24u), oshift = threadIdx.x & 24u;
+    // a subtree that fits into one node entirely (six wide nodes out of seven) is dissolved level by level, every
+    // internal child of a round at once: one dependent load per LEVEL instead of one per opening
+    const bool fits = act && __reduce_add_sync(omask, c.valid ? c.slots : 0u) <= 8u;
+    if (__any_sync(0xffffffffu, fits)) {
+        for (;;) {
+            const bool opening = fits && c.valid && !c.leaf;
+            const uint32_t om = (__ballot_sync(0xffffffffu, opening) >> oshift) & 0xffu;
+            if (!__any_sync(0xffffffffu, om != 0u)) break;
+            // lane k (opening) keeps the left half; lane nc + r takes the right half of the r-th opening lane
+            const int src = (l >= nc && l - nc < (uint32_t)__popc(om)) ? (int)__fns(om, 0u, (int)(l - nc) + 1) : (int)l;
+            const uint32_t id = __shfl_sync(0xffffffffu, c.id, src, 8);
+            if (opening) oct_set(c, &t.node[id].l);
+            else if (om && l >= nc && l - nc < (uint32_t)__popc(om)) oct_set(c, &t.node[id].r);
+            nc += (uint32_t)__popc(om);
+        }
+    }
+    if (__any_sync(0xffffffffu, act && !fits)) {
+        const bool gen = act && !fits;
+        // ---- open the largest child with more than 8 leaf slots until the node is full
+        for (;;) {
+            const bool cand = gen && nc < 8u && c.valid && !c.leaf && c.slots > 8u;
+            const uint32_t best = oct_argmax(cand ? __float_as_uint(c.area) + 1u : 0u, l, omask);
+            if (!__any_sync(0xffffffffu, best < 8u)) break;
+            oct_open(t, c, l, best < 8u, best & 7u, nc);
+        }
+        // ---- dissolve, smallest first, children whose whole subtree fits into the free slots
         uint32_t pending = 0u;
-        bool more = act;
+        bool more = gen;
         for (;;) {
             const bool cand = more && pending == 0u && c.valid && !c.leaf && nc - 1u + c.slots <= 8u;
-            const uint32_t best = oct_argmax(-(float)c.slots, cand, l);
+            const uint32_t best = oct_argmax(cand ? 0xffffffffu - c.slots : 0u, l, omask);
             if (more && pending == 0u) {
                 if (best < 8u) pending = 1u << best;
                 else more = false;
@@ -256,17 +280,19 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
         if (!(ddx == ddx)) ddx = 0.f;
         if (!(ddy == ddy)) ddy = 0.f;
         if (!(ddz == ddz)) ddz = 0.f;
+        float v[8];// this child's affinity to each slot (octant), constant over the rounds
+#pragma unroll
+        for (int s = 0; s < 8; s++) v[s] = ((s & 1) ? ddx : -ddx) + ((s & 2) ? ddy : -ddy) + ((s & 4) ? ddz : -ddz);
         uint32_t free_slots = 0xffu;
-        for (uint32_t round = 0u; round < 8u; round++) {
+        const uint32_t rounds = __reduce_max_sync(0xffffffffu, act ? nc : 0u);
+        for (uint32_t round = 0u; round < rounds; round++) {
             float bv = -INFINITY;
             int bs = -1;
 #pragma unroll
-            for (int s = 0; s < 8; s++) {
-                const float v = ((s & 1) ? ddx : -ddx) + ((s & 2) ? ddy : -ddy) + ((s & 4) ? ddz : -ddz);
-                if (((free_slots >> s) & 1u) && (v > bv || bs < 0)) bv = v, bs = s;
-            }
+            for (int s = 0; s < 8; s++)
+                if (((free_slots >> s) & 1u) && (v[s] > bv || bs < 0)) bv = v[s], bs = s;
             const bool cand = act && round < nc && c.valid && slot < 0;
-            const uint32_t who = oct_argmax(bv, cand, l);
+            const uint32_t who = oct_argmax(cand ? float_to_ordered(bv) : 0u, l, omask);
             const int ws = __shfl_sync(0xffffffffu, bs, (int)(who & 7u), 8);
             if (who < 8u) {
                 if (l == who) slot = ws;
@@ -276,14 +302,14 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
     }
     // ---- allocate internal children and primitive records
     const bool is_int = act && c.valid && !c.leaf, is_leaf = act && c.valid && c.leaf;
-    const uint32_t int_by_slot = oct_or(is_int ? (1u << slot) : 0u);
-    const uint32_t cnt_by_slot = oct_or(is_leaf ? (c.count << (2 * slot)) : 0u);// counts <= 3: two bits per slot
+    const uint32_t int_by_slot = oct_or(is_int ? (1u << slot) : 0u, omask);
+    const uint32_t cnt_by_slot = oct_or(is_leaf ? (c.count << (2 * slot)) : 0u, omask);// counts <= 3: two bits per slot
     const uint32_t n_int = (uint32_t)__popc(int_by_slot);
     const uint32_t n_prims = (uint32_t)__popc(cnt_by_slot & 0x5555u) + 2u * (uint32_t)__popc(cnt_by_slot & 0xaaaau);
     uint32_t child_base = 0u, prim_base = 0u;
     if (act && l == 0u) {
-        if (n_int) child_base = atomicAdd(&o.counters[0], n_int);
-        if (n_prims) prim_base = atomicAdd(&o.counters[1], n_prims);
+        if (n_int) child_base = atomicAdd(&o.counters[0 * COUNTER_STRIDE], n_int);
+        if (n_prims) prim_base = atomicAdd(&o.counters[1 * COUNTER_STRIDE], n_prims);
     }
     child_base = __shfl_sync(0xffffffffu, child_base, 0, 8), prim_base = __shfl_sync(0xffffffffu, prim_base, 0, 8);
     bool ok = true;
@@ -291,7 +317,7 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
         if (l == 0u) o.header->error = 1u;
         ok = false, act = false;
     }
-    // ---- per child: schedule the internal ones, gather the leaves, quantise the box
+    // ---- per child: schedule the internal ones, note the leaves' records, quantise the box
     Node8 *stage = reinterpret_cast<Node8 *>(node_smem) + (threadIdx.x >> 3);
     uint32_t *sw = reinterpret_cast<uint32_t *>(stage);
     const bool okx = nlx <= nhx, oky = nly <= nhy, okz = nlz <= nhz;
@@ -310,14 +336,13 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             const uint32_t w = child_base + (uint32_t)__popc(int_by_slot & ((1u << slot) - 1u));
             meta = (uint8_t)((1u << 5) | (24u + (uint32_t)slot));
             if (o.parent) o.parent[w] = (widx << 3) | (uint32_t)slot;
-            o.task[w] = c.id;
+            // one 64-bit store: a consumer that sees the node id also sees the depth
+            __stcg(reinterpret_cast<unsigned long long *>(&o.task[w]), ((unsigned long long)(depth + 1u) << 32) | c.id);
         } else {
             const uint32_t below = cnt_by_slot & ((1u << (2 * slot)) - 1u);
             const uint32_t po = (uint32_t)__popc(below & 0x5555u) + 2u * (uint32_t)__popc(below & 0xaaaau);
-            uint32_t pos[4];
-            const uint32_t cnt = gather_leaf(t, c.id, pos, 3u);
-            for (uint32_t q = 0; q < cnt; q++) o.rec_src[prim_base + po + q] = pos[q];
-            const uint32_t unary = cnt == 1u ? 1u : cnt == 2u ? 3u : 7u;
+            for (uint32_t q = 0; q < c.count; q++) o.rec_src[prim_base + po + q] = c.first + q;
+            const uint32_t unary = c.count == 1u ? 1u : c.count == 2u ? 3u : 7u;
             meta = (uint8_t)((unary << 5) | po);
         }
         stage->meta[slot] = meta;
@@ -340,71 +365,84 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             o.header->hi[0] = nhx, o.header->hi[1] = nhy, o.header->hi[2] = nhz;
             if (o.parent) o.parent[0] = INVALID_U32;
         }
-        if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2], n_prims);
+        if (n_prims && LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], n_prims) + n_prims == t.n) {
+            // the last primitive has its slot: every wide node has been processed
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(done_flag) = 1u;
+        }
     }
     __syncwarp();
     return ok;
 }
 
-// BVH2 -> BVH8, level by level inside ONE persistent kernel: the wide nodes of a level are the contiguous index range
-// allocated while the previous level was processed, so each level is a grid-stride loop over [begin, end) — one octet
-// of lanes per node while the level is narrow, one thread per node (collapse_node, lcrt_build.h) once it is wide; both
-// make identical decisions — followed by a grid-wide barrier (arrival counter + generation word; the last block to arrive
-// snapshots the node counter, which is the next level's `end`).  The grid never exceeds what is co-resident, so the
-// barrier can not deadlock; there is no polling on individual tasks.
+// BVH2 -> BVH8 in ONE persistent kernel without levels or grid barriers: wide node w is built by the octet (eight lanes)
+// that owns index w (round-robin over the grid), as soon as its parent has scheduled it (task[w], a 64-bit word written
+// with one store).  Indices are handed out by an atomic counter in the order nodes are opened, so a node's parent always
+// has a smaller index: the lowest unprocessed index is always ready, and with the whole grid co-resident (cooperative
+// launch) nothing can wait forever.  The last primitive to get its record slot raises `done`; octets whose next index was
+// never scheduled leave then.  (Round 1 ran level by level with a grid barrier per level: 0.58 ms at 1.3 M triangles.)
 template<class Input>
-__global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *bar, uint32_t *levels_out) {
+__global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *done_flag,
+                                                                                        uint32_t *levels_out) {
     __shared__ __align__(16) unsigned char node_smem[(COLLAPSE_BLOCK / 8) * sizeof(Node8)];
-    const uint32_t octets = COLLAPSE_BLOCK / 8u;
-    const uint32_t stride = gridDim.x * octets, goct = blockIdx.x * octets + (threadIdx.x >> 3);
-    __shared__ uint32_t s_end;
-    uint32_t begin = 0u, end = 1u, gen = 0u;
-    while (begin < end) {
-        if (end - begin <= stride * (uint32_t)LCRT_COLLAPSE_OCTET_WAVES) {
-            // narrow level: latency matters (the top of the tree is a chain of such levels) -> eight lanes per node
-            for (uint32_t base = begin; base < end; base += stride) {// warp-uniform trip count
-                const uint32_t w = base + goct;
-                bool act = w < end;
-                uint32_t bid = INVALID_U32;
-                if (act) bid = (w == 0u) ? *t.root : LCRT_VOLATILE_LOAD_U32(&o.task[w]);
-                if (act && bid == INVALID_U32) atomicExch(abort_flag, 1u), act = false;
-                if (!collapse_octet(t, o, in, w, bid, act, node_smem)) atomicExch(abort_flag, 1u);
+    __shared__ uint32_t s_depth;
+    if (threadIdx.x == 0) s_depth = 0u;
+    __syncthreads();
+    const uint32_t octets = COLLAPSE_BLOCK / 8u, stride = gridDim.x * octets, l = threadIdx.x & 7u;
+    uint32_t w = blockIdx.x * octets + (threadIdx.x >> 3);
+    bool finished = w >= o.node_capacity;
+    for (;;) {
+        // ---- wait until a task of this warp's four octets is there (or nothing will ever come): a tight loop, the polls of
+        // idle warps compete for issue slots with the warps that build nodes
+        unsigned long long word = 0xffffffffull;
+        uint32_t idle = 0u;
+        bool act = false;
+        for (;;) {
+            if (!finished) {
+                if (w == 0u) word = 1ull << 32;// the root: described by t.root, depth 1
+                else if (l == 0u) word = __ldcg(reinterpret_cast<const unsigned long long *>(&o.task[w]));
             }
-        } else {
-            // wide level: throughput matters -> one thread per node (eight times as many nodes in flight)
-            for (uint32_t w = begin + blockIdx.x * blockDim.x + threadIdx.x; w < end; w += gridDim.x * blockDim.x) {
-                const uint32_t bid = LCRT_VOLATILE_LOAD_U32(&o.task[w]);
-                if (bid == INVALID_U32 || !collapse_node(t, o, in, w, bid)) atomicExch(abort_flag, 1u);
+            const uint32_t ready = __ballot_sync(0xffffffffu, !finished && (uint32_t)word != INVALID_U32);
+            if (ready) {
+                act = ((ready >> (threadIdx.x & 24u)) & 1u) != 0u;
+                break;
             }
-        }
-        // ---- grid barrier (tasks and parents written above are released by the fence before the arrival)
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            __threadfence();
-            if (atomicAdd(&bar[0], 1u) == gridDim.x * (gen + 1u) - 1u) {
-                const uint32_t count = LCRT_VOLATILE_LOAD_U32(&o.counters[0]);
-                bar[2 + (gen & 1u)] = LCRT_VOLATILE_LOAD_U32(abort_flag) ? end : (count < o.node_capacity ? count : o.node_capacity);
-                __threadfence();
-                atomicExch(&bar[1], gen + 1u);
-            } else {
-                uint32_t polls = 0u;
-                while (LCRT_VOLATILE_LOAD_U32(&bar[1]) <= gen) {
-                    __nanosleep(20);
-                    if (++polls > (1u << 24)) {// safety net (never reached with a cooperative launch): give up, never hang
-                        atomicExch(abort_flag, 2u);
-                        break;
+            if ((++idle & 15u) == 0u) {
+                // nothing for a while: done / abort are raised after the last task has been written, so an index that is
+                // still empty behind them was never going to be scheduled (one more look at it, behind a fence)
+                const uint32_t stop = LCRT_VOLATILE_LOAD_U32(done_flag) | LCRT_VOLATILE_LOAD_U32(abort_flag);
+                if (stop) {
+                    __threadfence();
+                    if (!finished && l == 0u) word = __ldcg(reinterpret_cast<const unsigned long long *>(&o.task[w]));
+                    const uint32_t late = __ballot_sync(0xffffffffu, !finished && (uint32_t)word != INVALID_U32 && !LCRT_VOLATILE_LOAD_U32(abort_flag));
+                    if (late) {
+                        act = ((late >> (threadIdx.x & 24u)) & 1u) != 0u;
+                        finished = finished || !act;
+                    } else {
+                        finished = true;
                     }
+                    break;
+                }
+                if (idle > (1u << 22)) {// safety net (seconds): never hang the device, flag the build instead
+                    atomicExch(abort_flag, 2u);
+                    finished = true;
+                    break;
                 }
             }
-            __threadfence();
-            s_end = LCRT_VOLATILE_LOAD_U32(abort_flag) == 2u ? end : LCRT_VOLATILE_LOAD_U32(&bar[2 + (gen & 1u)]);
+            __nanosleep(idle < 16u ? 32u : 200u);
         }
-        __syncthreads();
-        gen++;
-        begin = end, end = s_end;
-        __syncthreads();
+        if (__all_sync(0xffffffffu, finished)) break;
+        word = __shfl_sync(0xffffffffu, word, (int)(threadIdx.x & 24u));
+        const uint32_t bid = (uint32_t)word, depth = (uint32_t)(word >> 32);
+        if (!collapse_octet(t, o, in, w, bid, depth, act, node_smem, done_flag)) atomicExch(abort_flag, 1u);
+        if (act) {
+            if (l == 0u) atomicMax(&s_depth, depth);
+            w += stride;
+            if (w >= o.node_capacity) finished = true;
+        }
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) levels_out[0] = gen;// one level per iteration: the depth of the wide hierarchy
+    __syncthreads();
+    if (threadIdx.x == 0 && s_depth) atomicMax(levels_out, s_depth);
 }
 
 template<class Input>
@@ -415,7 +453,7 @@ __global__ void __launch_bounds__(256) k_emit_records(Bvh2 t, Bvh8Out o, Input i
         // deepest instanced BLAS (one atomic per warp): the TLAS header records the stack a ray can need
         uint32_t d = 0u;
         if (j < t.n) {
-            const BlobHeader *h = InstInput::blas_of(in.inst[t.order[o.rec_src[j]]]);
+            const BlobHeader *h = InstInput::blas_of(in.inst[t.order(o.rec_src[j])]);
             if (h) d = h->depth;
         }
         d = __reduce_max_sync(0xffffffffu, d);
@@ -427,11 +465,11 @@ __global__ void __launch_bounds__(256) k_emit_records(Bvh2 t, Bvh8Out o, Input i
 // that is not updatable, 5 the hierarchy is deeper than the traversal stack (LCRT_STACK_SIZE)
 __global__ void k_build_finalize(BlobHeader *h, const uint32_t *small, uint32_t n) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        h->node_count = small[SM_COUNTERS + 0];
-        h->prim_written = small[SM_COUNTERS + 1];
+        h->node_count = small[SM_COUNTERS + 0 * COUNTER_STRIDE];
+        h->prim_written = small[SM_COUNTERS + 1 * COUNTER_STRIDE];
         h->depth = small[SM_LEVELS];
         h->max_stack = h->kind == KIND_INSTANCES ? small[SM_LEVELS] + 2u + small[SM_CHILD_DEPTH] : small[SM_LEVELS];
-        bool ok = small[SM_ABORT] == 0u && small[SM_COUNTERS + 2] == n && small[SM_COUNTERS + 0] <= h->node_capacity;
+        bool ok = small[SM_ABORT] == 0u && small[SM_COUNTERS + 2 * COUNTER_STRIDE] == n && small[SM_COUNTERS + 0 * COUNTER_STRIDE] <= h->node_capacity;
         uint32_t err = ok ? 0u : (small[SM_ABORT] ? small[SM_ABORT] : 3u);
         if (ok && h->max_stack > (uint32_t)LCRT_STACK_SIZE) ok = false, err = 5u;
         h->error = err;
@@ -751,6 +789,7 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     if (blob == nullptr || blob_bytes < L.total_bytes) return LCRT_ERROR_BUFFER_TOO_SMALL;
     if (temp == nullptr || temp_bytes < T.total_bytes) return LCRT_ERROR_BUFFER_TOO_SMALL;
     if ((reinterpret_cast<uintptr_t>(blob) & 127u) || (reinterpret_cast<uintptr_t>(temp) & 127u)) return LCRT_ERROR_MISALIGNED;
+    if (n > SORT_MAX_KEYS) return LCRT_ERROR_INVALID_VALUE;
     DeviceInfo *dev;
     if (int rc = device_info(&dev)) return rc;
     char *tp = static_cast<char *>(temp);
@@ -761,50 +800,54 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     LCRT_LAUNCH_CHECK("k_build_init");
     if (n == 0) return LCRT_SUCCESS;
     uint32_t *flag = reinterpret_cast<uint32_t *>(tp + T.flag);
-    uint32_t *task = reinterpret_cast<uint32_t *>(tp + T.task);
+    u2 *task = reinterpret_cast<u2 *>(tp + T.task);
+    // flag and task are adjacent in the scratch layout: arrival counters 0, tasks INVALID
     LCRT_CUDA(cudaMemsetAsync(flag, 0, (uint64_t)n * 4, stream));
-    LCRT_CUDA(cudaMemsetAsync(task, 0xff, (uint64_t)L.node_capacity * 4, stream));
+    LCRT_CUDA(cudaMemsetAsync(task, 0xff, (uint64_t)L.node_capacity * 8, stream));
     const uint32_t blocks256 = (n + 255u) / 256u;
+    f4 *pbox = reinterpret_cast<f4 *>(tp + T.pbox);
     {
-        const uint32_t g = blocks256 < (uint32_t)dev->sm_count * 8u ? blocks256 : (uint32_t)dev->sm_count * 8u;
-        k_centroid_bounds<Input><<<g, 256, 0, stream>>>(in, small);
-        LCRT_LAUNCH_CHECK("k_centroid_bounds");
+        const uint32_t g = blocks256 < (uint32_t)dev->sm_count * 16u ? blocks256 : (uint32_t)dev->sm_count * 16u;
+        k_prim_bounds<Input><<<g, 256, 0, stream>>>(in, pbox, small);
+        LCRT_LAUNCH_CHECK("k_prim_bounds");
     }
     SortBuffers sb;
     sb.keys[0] = reinterpret_cast<uint64_t *>(tp + T.keys0), sb.keys[1] = reinterpret_cast<uint64_t *>(tp + T.keys1);
-    sb.vals[0] = reinterpret_cast<uint32_t *>(tp + T.vals0), sb.vals[1] = reinterpret_cast<uint32_t *>(tp + T.vals1);
-    sb.table = reinterpret_cast<uint32_t *>(tp + T.hist);
-    sb.sums = sb.table + 256ull * T.sort_blocks;
-    const uint32_t bits = morton_bits_for(n);
-    k_morton<Input><<<blocks256, 256, 0, stream>>>(in, small, sb.keys[0], sb.vals[0], bits);
+    sb.vals[0] = sb.vals[1] = nullptr;
+    sb.control = reinterpret_cast<uint32_t *>(tp + T.control);
+    const uint32_t bits = morton_bits_for(n), index_bits = index_bits_for(n);
+    k_morton<<<blocks256, 256, 0, stream>>>(pbox, n, small, sb.keys[0], bits, index_bits);
     LCRT_LAUNCH_CHECK("k_morton");
-    const int cur = radix_sort_pairs(stream, sb, n, 3u * bits);
-    LCRT_LAUNCH_CHECK("radix_sort_pairs");
+    const int cur = radix_sort(stream, sb, n, index_bits, 3u * bits, dev->sm_count);
+    if (cur < 0) return LCRT_ERROR_INVALID_VALUE;
+    LCRT_LAUNCH_CHECK("radix_sort");
     Bvh2 t;
-    t.n = n, t.keys = sb.keys[cur], t.order = sb.vals[cur];
-    t.lo = reinterpret_cast<f4 *>(tp + T.lo), t.hi = reinterpret_cast<f4 *>(tp + T.hi);
-    t.child = reinterpret_cast<u2 *>(tp + T.child), t.range = reinterpret_cast<u2 *>(tp + T.range);
-    t.flag = flag, t.root = small + SM_ROOT, t.ci = sah_ci(flags), t.max_leaf = Input::max_leaf;
-    k_climb<Input><<<blocks256, 256, 0, stream>>>(t, in);
+    t.n = n, t.index_bits = index_bits, t.keys = sb.keys[cur];
+    t.node = reinterpret_cast<Bvh2Node *>(tp + T.node);
+    t.flag = flag, t.root = reinterpret_cast<Bvh2Half *>(small + SM_ROOT_HALF), t.ci = sah_ci(flags), t.max_leaf = Input::max_leaf;
+    // 64-thread blocks: a block lives as long as its longest climber (most threads leave after one or two levels)
+    k_climb<<<(n + 63u) / 64u, 64, 0, stream>>>(t, pbox);
     LCRT_LAUNCH_CHECK("k_climb");
     Bvh8Out o;
     o.header = h, o.nodes = reinterpret_cast<Node8 *>(bp + L.nodes_offset), o.prims = bp + L.prims_offset;
     o.parent = L.parent_offset ? reinterpret_cast<uint32_t *>(bp + L.parent_offset) : nullptr;
     o.task = task, o.counters = small + SM_COUNTERS, o.node_capacity = L.node_capacity;
-    o.rec_src = sb.vals[cur ^ 1];// the idle half of the sort's ping-pong buffers
+    o.rec_src = reinterpret_cast<uint32_t *>(sb.keys[cur ^ 1]);// the idle half of the sort's ping-pong buffers
     {
         int &bps = dev->collapse_blocks_per_sm[Input::kind];
         if (bps == 0) {
             LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_collapse<Input>, COLLAPSE_BLOCK, 0));
             if (bps < 1) bps = 1;
+            static const char *cap = getenv("LCRT_COLLAPSE_BLOCKS_PER_SM");// developer knob (tools/build_perf.py sweeps it)
+            if (cap && atoi(cap) > 0 && atoi(cap) < bps) bps = atoi(cap);
         }
         uint32_t g = (uint32_t)(dev->sm_count * bps);
         const uint32_t need = (L.node_capacity + COLLAPSE_BLOCK / 8u - 1u) / (COLLAPSE_BLOCK / 8u);
         if (g > need) g = need;
-        // cooperative launch: the runtime guarantees that all blocks are co-resident (the kernel has a grid barrier)
-        uint32_t *abort_flag = small + SM_ABORT, *bar = small + SM_BARRIER, *levels = small + SM_LEVELS;
+        // cooperative launch: the runtime guarantees that all blocks are co-resident (octets wait for their parents' tasks)
+        uint32_t *abort_flag = small + SM_ABORT, *done_flag = small + SM_DONE, *levels = small + SM_LEVELS;
         Input in_arg = in;
-        void *args[] = {&t, &o, &in_arg, &abort_flag, &bar, &levels};
+        void *args[] = {&t, &o, &in_arg, &abort_flag, &done_flag, &levels};
         LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(COLLAPSE_BLOCK), args, 0, stream));
     }
     k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in, small + SM_CHILD_DEPTH);
@@ -1016,24 +1059,25 @@ int lcrtBlobGetInfo(lcrtStream stream, const void *blob, lcrtBlobInfo *out) {
 
 uint64_t lcrtSortTempBytes(uint32_t n) {
     const uint64_t nn = n ? n : 1;
-    return align_up(nn * 8, 256) + align_up(nn * 4, 256) + align_up(sort_table_bytes(n), 256);
+    return align_up(nn * 8, 256) + align_up(nn * 4, 256) + align_up(sort_control_bytes(n), 256);
 }
 
 int lcrtSortPairs(lcrtStream stream_, uint64_t *keys, uint32_t *values, uint32_t n, uint32_t key_bits, void *temp, uint64_t temp_bytes) {
     if (n == 0) return LCRT_SUCCESS;
-    if (keys == nullptr || values == nullptr || temp == nullptr || key_bits == 0 || key_bits > 64) return LCRT_ERROR_INVALID_VALUE;
+    if (keys == nullptr || values == nullptr || temp == nullptr || key_bits == 0 || key_bits > 64 || n > SORT_MAX_KEYS) return LCRT_ERROR_INVALID_VALUE;
     if (temp_bytes < lcrtSortTempBytes(n)) return LCRT_ERROR_BUFFER_TOO_SMALL;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    DeviceInfo *dev;
+    if (int rc = device_info(&dev)) return rc;
     char *tp = static_cast<char *>(temp);
     SortBuffers sb;
     sb.keys[0] = keys, sb.vals[0] = values;
     sb.keys[1] = reinterpret_cast<uint64_t *>(tp);
     sb.vals[1] = reinterpret_cast<uint32_t *>(tp + align_up((uint64_t)n * 8, 256));
-    sb.table = reinterpret_cast<uint32_t *>(tp + align_up((uint64_t)n * 8, 256) + align_up((uint64_t)n * 4, 256));
-    const uint32_t ntiles = (n + SORT_TILE_KEYS - 1) / SORT_TILE_KEYS;
-    sb.sums = sb.table + 256ull * ntiles;
-    const int cur = radix_sort_pairs(stream, sb, n, key_bits);
-    LCRT_LAUNCH_CHECK("radix_sort_pairs");
+    sb.control = reinterpret_cast<uint32_t *>(tp + align_up((uint64_t)n * 8, 256) + align_up((uint64_t)n * 4, 256));
+    const int cur = radix_sort(stream, sb, n, 0u, key_bits, dev->sm_count);
+    if (cur < 0) return LCRT_ERROR_INVALID_VALUE;
+    LCRT_LAUNCH_CHECK("radix_sort");
     if (cur == 1) {
         LCRT_CUDA(cudaMemcpyAsync(keys, sb.keys[1], (uint64_t)n * 8, cudaMemcpyDeviceToDevice, stream));
         LCRT_CUDA(cudaMemcpyAsync(values, sb.vals[1], (uint64_t)n * 4, cudaMemcpyDeviceToDevice, stream));

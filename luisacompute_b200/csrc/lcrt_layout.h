@@ -35,17 +35,24 @@ inline BlobLayout blob_layout(uint32_t kind, uint32_t prim_count, uint32_t flags
 
 // scratch for one build of n primitives
 struct TempLayout {
-    uint64_t keys0, keys1, vals0, vals1;      // radix sort ping-pong
-    uint64_t hist;                            // per-block digit histograms (one pass at a time)
-    uint64_t lo, hi, child, range, flag;      // binary hierarchy
-    uint64_t task;                            // wide-node work items
-    uint64_t small;                           // centroid bounds (6 ordered uints), root id, counters[3]
+    uint64_t small;                           // SMALL_WORDS u32: centroid bounds, counters, control words, the root half
+    uint64_t flag;                            // [n] arrival counters of the binary nodes
+    uint64_t task;                            // [node_capacity] u2 wide-node work items
+    uint64_t keys0, keys1;                    // radix sort ping-pong (u64 keys = Morton << index_bits | primitive)
+    uint64_t control;                         // sort histograms / tickets / look-back words
+    uint64_t pbox;                            // [n] 2 x f4 primitive boxes in input order
+    uint64_t node;                            // [n] 96-byte binary nodes
     uint64_t total_bytes;
-    uint32_t sort_blocks;
 };
 
 constexpr uint32_t SORT_TILE = 4096;     // keys per block per pass (256 threads x 16)
-constexpr uint32_t SMALL_WORDS = 32;
+constexpr uint32_t SORT_CONTROL_PASSES = 8;
+constexpr uint32_t SMALL_WORDS = 256;
+
+inline uint64_t sort_control_bytes_for(uint32_t n) {// == sort_control_bytes() of lcrt_sort.cuh (static_assert'ed in lcrt_kernels.cu)
+    const uint64_t tiles = ((uint64_t)(n ? n : 1u) + SORT_TILE - 1) / SORT_TILE;
+    return ((uint64_t)SORT_CONTROL_PASSES * 256u + SORT_CONTROL_PASSES + 64u + (uint64_t)SORT_CONTROL_PASSES * tiles * 256u) * 4u;
+}
 
 inline TempLayout temp_layout(uint32_t n, uint32_t node_capacity) {
     TempLayout t;
@@ -56,18 +63,13 @@ inline TempLayout temp_layout(uint32_t n, uint32_t node_capacity) {
         off = align_up(off + bytes, 256);
         return o;
     };
-    t.sort_blocks = (uint32_t)((nn + SORT_TILE - 1) / SORT_TILE);
     t.small = take(SMALL_WORDS * 4);
-    t.flag = take(nn * 4);// zeroed together with `small` and `task`... (see build: one memset each)
-    t.task = take((uint64_t)node_capacity * 4);
+    t.flag = take(nn * 4);
+    t.task = take((uint64_t)node_capacity * 8);
     t.keys0 = take(nn * 8), t.keys1 = take(nn * 8);
-    t.vals0 = take(nn * 4), t.vals1 = take(nn * 4);
-    {
-        const uint64_t m = 256ull * t.sort_blocks;
-        t.hist = take((m + (m + 2047) / 2048 + 64) * 4);// digit-major table followed by the scan's tile sums
-    }
-    t.lo = take((2 * nn) * 16), t.hi = take((2 * nn) * 16);
-    t.child = take(nn * 8), t.range = take(nn * 8);
+    t.control = take(sort_control_bytes_for(n));
+    t.pbox = take(nn * 32);
+    t.node = take(nn * 96);
     t.total_bytes = off;
     return t;
 }

@@ -82,3 +82,59 @@ def bind_to_gpu_numa(device_index: int):
     except Exception:
         return None
 
+
+
+class HitGatherer:
+    """Gather of tile-sharded 24-byte hit records into RAY ORDER on `dst`, chunk by chunk, overlapped with tracing.
+
+    The local batch of every rank is `n_local_tiles` tiles of `tile` rays; local tile t of rank r is global tile
+    t * world + r (tiles dealt round-robin).  `submit(chunk, t0, t1, after)` queues the gather of the local
+    tiles [t0, t1) on a high-priority side stream behind the CUDA event `after` (recorded when the chunk's trace has been
+    enqueued), so the NCCL transfer and the reorder copy of chunk c run while chunk c + 1 is being traced.  `dst` receives
+    into a double-buffered staging area [world, chunk] and one strided copy per chunk puts the records into the
+    framebuffer `full` ([n_local_tiles, world, tile * 6] == ray order).  `finish()` makes the caller's stream wait for the
+    side stream.  Works with any backend (CPU tensors / gloo run inline)."""
+
+    def __init__(self, n_local_tiles: int, device, chunk_tiles: int = 8, tile: int = TILE, dst: int = 0, words: int = 6):
+        import torch
+        import torch.distributed as dist
+        self.rank, self.world, self.dst = dist.get_rank(), dist.get_world_size(), dst
+        self.tile, self.words, self.chunk_tiles, self.n_local_tiles = tile, words, chunk_tiles, n_local_tiles
+        self.device = torch.device(device)
+        self.cuda = self.device.type == "cuda"
+        self.comm = torch.cuda.Stream(self.device, priority=-1) if self.cuda else None
+        self.full = None
+        self.stage = None
+        if self.rank == dst:
+            self.full = torch.empty((n_local_tiles, self.world, tile * words), dtype=torch.int32, device=self.device)
+            self.stage = [torch.empty((self.world, chunk_tiles * tile, words), dtype=torch.int32, device=self.device) for _ in range(2)]
+        self._k = 0
+
+    def _ctx(self):
+        import contextlib
+        import torch
+        return torch.cuda.stream(self.comm) if self.cuda else contextlib.nullcontext()
+
+    def submit(self, chunk, t0: int, t1: int, after=None):
+        import torch.distributed as dist
+        n = (t1 - t0) * self.tile
+        assert chunk.shape[0] == n and t1 - t0 <= self.chunk_tiles
+        with self._ctx():
+            if self.cuda and after is not None:
+                self.comm.wait_event(after)
+            if self.rank == self.dst:
+                st = self.stage[self._k & 1]
+                dist.gather(chunk, [st[r, :n] for r in range(self.world)], self.dst)
+                self.full[t0:t1].copy_(st[:, :n].reshape(self.world, t1 - t0, self.tile * self.words).transpose(0, 1))
+            else:
+                dist.gather(chunk, None, self.dst)
+        self._k += 1
+
+    def finish(self):
+        import torch
+        if self.cuda:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm)
+
+    def framebuffer(self):
+        """[n_rays, words] in ray order (dst only)."""
+        return None if self.full is None else self.full.view(-1, self.words)

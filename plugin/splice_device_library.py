@@ -6,9 +6,14 @@ the generated code calls are this repository's (lcrtDeviceLibrarySource(): lcrt_
 lcrt_device_library.cuh over the BVH8 format) instead of OptiX hit-object traversal:
 
   * `struct alignas(16) LCRay` ... `lc_accel_set_instance_user_id`   (cuda_device_resource.h:1279-1510)  -> our library
-  * inside `#ifdef LUISA_ENABLE_OPTIX` (:1553-2387): everything except the launch-index helpers (lc_dispatch_id,
-    lc_dispatch_size, lc_kernel_id, lc_thread_id, lc_block_id, :1844-1880) is dropped; empty `__intersection__ray_query` /
-    `__anyhit__ray_query` entry points keep the reference's OptiX pipeline creation (cuda_shader_optix.cpp:190-265) happy.
+  * inside `#ifdef LUISA_ENABLE_OPTIX` (:1553-2387): everything is dropped.  A kernel that traces rays is ordinary device
+    code here, so the branch gets the launch-index helpers of the reference's NATIVE branch (:2391-2416: blockIdx / threadIdx,
+    `params.ls_kid`, lc_synchronize_block) — the generated `extern "C" __global__ void __raygen__main()` reading
+    `__constant__ Params params` is then launched with cuLaunchKernel by plugin/hybrid/b200_shader_rt.cpp, no OptiX
+    module / pipeline / SBT / optixLaunch (cuda_shader_optix.cpp:49-309, 478-483).  The code generator emits no
+    out-of-range guard for RT kernels (cuda_codegen_ast.cpp:1470-1472: OptiX launches exactly dispatch_size threads), so
+    `lc_dispatch_id()` — used exactly once, in `const auto did = lc_dispatch_id();` (:1504) right after `ls` — becomes a macro
+    that also returns from threads outside the dispatch, the same test the native branch's kernels carry.
 Nothing of the reference is stored in this repository: the input is read from the reference tree (or from a kernel source the
 reference dumped with LUISA_DUMP_SOURCE=1) at build / test time.
 usage: python plugin/splice_device_library.py IN OUT [--library FILE]   (IN: cuda_device_resource.h or a dumped kernel_*.cu)
@@ -42,22 +47,35 @@ def _end_of_function(text: str, start: int) -> int:
         i += 1
 
 
-def splice(text: str, library: str) -> str:
+def splice(text: str, library: str, native_launch: bool = True) -> str:
     a = text.index(RT_BEGIN)
     b = _end_of_function(text, text.index(RT_END_FN))
     o = text.index(OPTIX_BEGIN, b)
     g0 = text.index(GLUE_BEGIN, o)
     g1 = _end_of_function(text, text.index(GLUE_END_FN, g0))
     n = text.index(NATIVE_BEGIN, g1)
+    # the native branch's helpers, taken from the reference text at build time: "#else" ... up to its "#endif"
+    nat0 = n + len("#else\n")
+    nat1 = text.index("\n#endif", text.index("lc_synchronize_block", nat0))
+    native = text[nat0:nat1].replace("inline auto lc_dispatch_id() noexcept", "inline auto lc_native_dispatch_id() noexcept")
+    assert "lc_native_dispatch_id" in native and "threadIdx" in native and "_optix_" not in native
     optix_branch = (
         "#ifdef LUISA_ENABLE_OPTIX\n\n"
-        "// launch-index helpers of the reference (OptiX launches the kernel as a raygen program); the traversal is ordinary device code\n"
-        + text[g0:g1] + "\n\n"
-        "inline void lc_shader_execution_reorder(lc_uint hint, lc_uint hint_bits) noexcept {}\n\n"
-        "#ifdef LUISA_ENABLE_OPTIX_RAY_QUERY\n"
-        "extern \"C\" __global__ void __intersection__ray_query() {}\n"
-        "extern \"C\" __global__ void __anyhit__ray_query() {}\n"
-        "#endif\n\n")
+        "// ray-tracing kernels are launched natively (cuLaunchKernel): launch-index helpers of the reference's native branch\n"
+        + native + "\n\n"
+        "// the code generator emits no out-of-range guard for ray-tracing kernels: `const auto did = lc_dispatch_id();` gets it here\n"
+        "#define lc_dispatch_id() lc_native_dispatch_id(); if (lc_any(did >= ls)) { return; } static_cast<void>(0)\n\n")
+    if not native_launch:
+        # developer variant (plugin/hybrid/build.sh HYBRID_OPTIX_LAUNCH=1 -> lc-backend-b200o): the kernel stays an OptiX raygen
+        # program launched by the reference's CUDAShaderOptiX, only the traversal is ours — used to tell launch-path effects
+        # from traversal effects
+        optix_branch = (
+            "#ifdef LUISA_ENABLE_OPTIX\n\n" + text[g0:g1] + "\n\n"
+            "inline void lc_shader_execution_reorder(lc_uint hint, lc_uint hint_bits) noexcept {}\n\n"
+            "#ifdef LUISA_ENABLE_OPTIX_RAY_QUERY\n"
+            "extern \"C\" __global__ void __intersection__ray_query() {}\n"
+            "extern \"C\" __global__ void __anyhit__ray_query() {}\n"
+            "#endif\n\n")
     return text[:a] + "// ---- RT section: luisacompute_b200 device library (BVH8 traversal), spliced in by plugin/splice_device_library.py\n" + library + "\n" + \
         text[b:o] + optix_branch + text[n:]
 

@@ -37,3 +37,30 @@ def check_closest(oracle, oa, da, rays, mask=0xFF, allow_soft=0):
     assert res["t_bad"] == 0 and res["bary_bad"] == 0, res
     assert res["tie"] + res["grazing"] <= allow_soft, res
     return res, got
+
+
+def compare_query(oa, rays, e, g, t_rel=1e-5, bary_abs=1e-4):
+    """RayQuery (CommittedHit) records of the device `g` against the oracle's `e` under the BASELINE.json rule: hit type,
+    inst and prim exact, except surface hits whose claimed (inst, prim) the oracle evaluates to a hit within `t_rel` of its own
+    nearest t (two coplanar walls meeting in an edge: the tie rule); t within t_rel, barycentrics within bary_abs."""
+    same = (e["hit_type"] == g["hit_type"]) & (e["inst"] == g["inst"]) & ((e["prim"] == g["prim"]) | (e["hit_type"] == 0))
+    res = {"n": len(rays), "exact": int(np.count_nonzero(same)), "tie": 0, "bad": 0, "bad_index": []}
+    for i in np.nonzero(~same)[0]:
+        ok = False
+        if e["hit_type"][i] == 1 and g["hit_type"][i] == 1:
+            valid, ev = oa.eval_hit(rays[i:i + 1], g["inst"][i], g["prim"][i])
+            te = float(e["t"][i])
+            ok = bool(valid) and ev[3] >= -bary_abs and abs(ev[0] - te) <= t_rel * abs(te) and abs(float(g["t"][i]) - ev[0]) <= t_rel * abs(ev[0])
+        if ok:
+            res["tie"] += 1
+        else:
+            res["bad"] += 1
+            if len(res["bad_index"]) < 16:
+                res["bad_index"].append(int(i))
+    hit = same & (e["hit_type"] != 0)
+    rel = np.abs(g["t"][hit].astype(np.float64) - e["t"][hit].astype(np.float64)) / np.maximum(np.abs(e["t"][hit].astype(np.float64)), 1e-30)
+    res["t_bad"] = int(np.count_nonzero(rel > t_rel))
+    surf = same & (e["hit_type"] == 1)
+    db = np.abs(g["bary"][surf].astype(np.float64) - e["bary"][surf].astype(np.float64))
+    res["bary_bad"] = int(np.count_nonzero(db.max(axis=1) > bary_abs)) if len(db) else 0
+    return res

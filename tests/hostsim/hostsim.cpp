@@ -68,17 +68,17 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
         inv_ext[a] = ext > 0.f ? 1.0f / ext : 0.f;
         if (cb[a] == 0xffffffffu) clo[a] = 0.f, inv_ext[a] = 0.f;
     }
-    std::vector<uint64_t> keys(n);
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; i++) keys[i] = morton63(in.box(i), clo, inv_ext, morton_bits_for(n)), order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    // keys = Morton << index_bits | primitive; the device sorts the Morton bits with a stable sort starting from index order
+    const uint32_t bits = morton_bits_for(n), index_bits = index_bits_for(n);
     std::vector<uint64_t> skeys(n);
-    for (uint32_t i = 0; i < n; i++) skeys[i] = keys[order[i]];
-    std::vector<f4> lo(2 * n), hi(2 * n);
-    std::vector<u2> child(n), range(n);
+    for (uint32_t i = 0; i < n; i++) skeys[i] = (morton63(in.box(i), clo, inv_ext, bits) << index_bits) | (uint64_t)i;
+    std::sort(skeys.begin(), skeys.end());
+    std::vector<Bvh2Node> node(n);
     std::vector<uint32_t> flag(n, 0u);
-    uint32_t root = INVALID_U32;
-    Bvh2 t{n, skeys.data(), order.data(), lo.data(), hi.data(), child.data(), range.data(), flag.data(), &root, ci, Input::max_leaf};
+    Bvh2Half root;
+    memset(&root, 0, sizeof(root));
+    root.id = INVALID_U32;
+    Bvh2 t{n, index_bits, skeys.data(), node.data(), flag.data(), &root, ci, Input::max_leaf};
     // scrambled thread order: the algorithm must not depend on scheduling
     std::vector<uint32_t> perm(n);
     for (uint32_t i = 0; i < n; i++) perm[i] = i;
@@ -87,34 +87,35 @@ int build_blob(const Input &in, uint32_t flags, float ci, char *blob) {
         s = s * 1664525u + 1013904223u;
         std::swap(perm[i - 1], perm[(s >> 8) % i]);
     }
-    for (uint32_t k = 0; k < n; k++) lbvh_climb(t, perm[k], in.box(order[perm[k]]));
-    if (root == INVALID_U32) return -10;
-    std::vector<uint32_t> task(L.node_capacity, INVALID_U32);
-    uint32_t counters[3] = {1u, 0u, 0u};
+    for (uint32_t k = 0; k < n; k++) lbvh_climb(t, perm[k], in.box(t.order(perm[k])));
+    if (root.id == INVALID_U32) return -10;
+    if (root.first != 0u || root.last != n - 1u || (root.count_mark & ~LEAF_MARK) != n) return -10;
+    std::vector<u2> task(L.node_capacity, make_u2(INVALID_U32, 0u));
+    uint32_t counters[3 * COUNTER_STRIDE] = {};
+    counters[0] = 1u;
     std::vector<uint32_t> rec_src(n, INVALID_U32);
     Bvh8Out o{h, nodes, blob + L.prims_offset, L.parent_offset ? reinterpret_cast<uint32_t *>(blob + L.parent_offset) : nullptr, task.data(),
               rec_src.data(), counters, L.node_capacity};
-    task[0] = root;
-    // level by level, as k_collapse does: the wide nodes allocated while one level is processed are the next level
+    task[0] = make_u2(root.id, 1u);
+    // in index order, as the device's octets take them (a node's parent always has a smaller index); the deepest node gives
+    // the depth the header records
     uint32_t levels = 0;
-    for (uint32_t begin = 0, end = 1; begin < end; levels++) {
-        for (uint32_t w = begin; w < end; w++) {
-            if (task[w] == INVALID_U32) return -11;
-            if (!collapse_node(t, o, in, w, task[w])) return -12;
-        }
-        begin = end, end = counters[0];
+    for (uint32_t w = 0; w < counters[0]; w++) {
+        if (w && task[w].x == INVALID_U32) return -11;
+        if (!collapse_node(t, o, in, w, task[w].x, task[w].y)) return -12;
+        levels = std::max(levels, task[w].y);
     }
     h->depth = levels, h->max_stack = levels;
     if (Input::kind == KIND_INSTANCES) {
         h->max_stack = levels + 2u + deepest_blas(in);
         if (h->max_stack > (uint32_t)LCRT_STACK_SIZE) return -15;
     }
-    if (counters[2] != n || counters[1] != n) return -13;
+    if (counters[2 * COUNTER_STRIDE] != n || counters[1 * COUNTER_STRIDE] != n) return -13;
     for (uint32_t j = 0; j < n; j++) {
         if (rec_src[j] == INVALID_U32) return -14;
         emit_record(t, o, in, j);
     }
-    h->node_count = counters[0], h->prim_written = counters[1], h->built = 1;
+    h->node_count = counters[0], h->prim_written = counters[1 * COUNTER_STRIDE], h->built = 1;
     return 0;
 }
 

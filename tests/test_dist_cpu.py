@@ -39,7 +39,22 @@ def _worker(rank, world, port, ret):
         local[:, 0] = torch.from_numpy(idx).int()          # "hit" = the global ray index
         full = D.gather_hits(local, n, 0, tile=64)
         ok_gather = True if rank != 0 else bool(torch.equal(full[:, 0], torch.arange(n, dtype=torch.int32)))
-        ret[rank] = ok_blob and ok_gather
+        # the pipelined gatherer bench.py times: 6 local tiles of 16 rays per rank, chunks of 4 + 2 tiles
+        tile, tl = 16, 6
+        g = D.HitGatherer(tl, "cpu", chunk_tiles=4, tile=tile)
+        gidx = (torch.arange(tl)[:, None] * world + rank) * tile + torch.arange(tile)[None, :]      # global ray index of every local ray
+        local = torch.zeros((tl * tile, 6), dtype=torch.int32)
+        local[:, 0] = gidx.reshape(-1).int()
+        local[:, 5] = rank
+        for t0, t1 in ((0, 4), (4, 6)):
+            g.submit(local[t0 * tile:t1 * tile], t0, t1)
+        g.finish()
+        fb = g.framebuffer()
+        ok_pipe = True
+        if rank == 0:
+            ok_pipe = bool(torch.equal(fb[:, 0], torch.arange(tl * tile * world, dtype=torch.int32)))
+            ok_pipe = ok_pipe and bool(torch.equal(fb[:, 5].view(tl, world, tile)[:, 1], torch.ones((tl, tile), dtype=torch.int32)))
+        ret[rank] = ok_blob and ok_gather and ok_pipe
     finally:
         dist.destroy_process_group()
 

@@ -20,7 +20,7 @@ import pytest
 
 import luisacompute_b200 as lc
 from luisacompute_b200 import scenes as S
-from tests.gpu_util import build_pair
+from tests.gpu_util import build_pair, compare_query
 
 pytestmark = pytest.mark.gpu
 
@@ -134,11 +134,11 @@ def test_c5_fullsize(oracle, dev):
     rays = S.pinhole_rays(w, h, pos=(0.0, 0.0, 3.4), vfov_deg=38)
     e = oa.query(rays, 0xFF, False, 0, 0)
     g = lc.chits_to_numpy(da.query_all(rays, tri_program=0, proc_program=0))
-    assert np.array_equal(e["hit_type"], g["hit_type"]) and np.array_equal(e["inst"], g["inst"])
+    r1 = compare_query(oa, rays, e, g)
+    print(f"C5 first hit 1920x1080: {r1}")
+    # exact ties only where two walls (different instances) meet in an edge that a row or column of pixel centres hits exactly (618 at this size)
+    assert r1["bad"] == 0 and r1["t_bad"] == 0 and r1["bary_bad"] == 0 and r1["tie"] <= 2048, r1
     hit = e["hit_type"] != 0
-    assert np.array_equal(e["prim"][hit], g["prim"][hit])
-    np.testing.assert_allclose(g["t"][hit], e["t"][hit], rtol=1e-5)
-    np.testing.assert_allclose(g["bary"][hit], e["bary"][hit], atol=1e-4)
     assert np.count_nonzero(e["hit_type"] == 2) > 20000 and np.count_nonzero(e["hit_type"] == 1) > 1_000_000
     # one bounce: incoherent rays leaving the first hits (cosine-free uniform directions, seeded)
     t = np.where(hit, e["t"], 1.0).astype(np.float64)
@@ -150,13 +150,12 @@ def test_c5_fullsize(oracle, dev):
     b["o"], b["d"], b["tmin"], b["tmax"] = p.astype(np.float32), d2.astype(np.float32), 1e-4, S.FLT_MAX
     e2 = oa.query(b, 0xFF, False, 0, 0)
     g2 = lc.chits_to_numpy(da.query_all(b, tri_program=0, proc_program=0))
-    same = (e2["hit_type"] == g2["hit_type"]) & (e2["inst"] == g2["inst"]) & ((e2["prim"] == g2["prim"]) | (e2["hit_type"] == 0))
-    nd = int(np.count_nonzero(~same))
-    print(f"C5 bounce: {len(b)} rays, {nd} decisions differ (rays starting on a wall grazing that wall's own plane)")
-    # rays that start ON a wall may graze its own plane: those decisions are inside the tie tolerance by construction
-    assert nd <= 20 * (w * h) // (240 * 135) // 8, nd
-    ok = same & (e2["hit_type"] != 0)
-    np.testing.assert_allclose(g2["t"][ok], e2["t"][ok], rtol=1e-5, atol=1e-9)
+    r2 = compare_query(oa, b, e2, g2)
+    print(f"C5 bounce 1920x1080: {r2}")
+    # rays that start ON a wall (t = 1e-4 from its own plane, edges shared with the neighbouring walls) may differ inside the
+    # tie band; anything else is a mismatch
+    assert r2["bad"] == 0 and r2["t_bad"] == 0 and r2["tie"] <= 400, r2
+    nd = r2["tie"]
     # shadow-style query_any on the bounce rays: hit / miss only (D5)
     ea = oa.query(b, 0xFF, True, 0, 0)
     ga = lc.chits_to_numpy(da.query_any(b))

@@ -118,6 +118,7 @@ __device__ inline V3 offset_ray_origin(V3 p, V3 n) {
 extern "C" __global__ void __launch_bounds__(256, 2) k_c5_path_trace(C5Params params) {
     const uint32_t x = blockIdx.x * 16u + (threadIdx.x & 15u), y = blockIdx.y * 16u + (threadIdx.x >> 4);
     if (x >= params.w || y >= params.h) return;
+    const uint32_t live = __activemask();// the lanes of this warp that trace (converged here); used by the ray-count reduction at the end
     const uint32_t pix = y * params.w + x;
     uint32_t state = params.seeds[pix];
     if (state == 0u) state = tea(x, y);
@@ -232,9 +233,12 @@ extern "C" __global__ void __launch_bounds__(256, 2) k_c5_path_trace(C5Params pa
     float4 acc = params.image[pix];
     acc.x += fminf(radiance.x, 30.f * params.spp), acc.y += fminf(radiance.y, 30.f * params.spp), acc.z += fminf(radiance.z, 30.f * params.spp), acc.w += (float)params.spp;
     params.image[pix] = acc;
-    // one atomic per warp
-    for (int o = 16; o > 0; o >>= 1) rays += __shfl_xor_sync(__activemask(), rays, o);
-    if ((threadIdx.x & 31u) == 0u) atomicAdd(params.ray_counter, (unsigned long long)rays);
+    // one atomic per warp: reconverge the lanes that entered together first (__activemask() at this point is whatever subset
+    // the scheduler happens to run together after the divergent loop, which silently dropped counts)
+    __syncwarp(live);
+    uint32_t total = 0u;
+    for (uint32_t m = live; m; m &= m - 1u) total += __shfl_sync(live, rays, __ffs((int)m) - 1);
+    if ((threadIdx.x & 31u) == (uint32_t)(__ffs((int)live) - 1)) atomicAdd(params.ray_counter, (unsigned long long)total);
 }
 
 extern "C" __attribute__((visibility("default"))) int c5_render(void *stream, uint64_t handle, void *instances, const void *aabbs, const void *tri_verts,

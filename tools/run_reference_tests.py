@@ -1,8 +1,9 @@
 """Developer tool (GPU box): the reference's OWN test programs, compiled unmodified from /root/reference/src/tests
 (test_rtx.cpp: animated triangle, in-kernel set_instance_transform, BLAS refit + TLAS update per frame, 1024 frames;
 test_procedural.cpp: AABB spheres + a mesh through RayQuery handlers), run once with the reference's `cuda` backend (OptiX)
-and once with `b200` (the same backend with this repository's BVH builder, host layer and device-library traversal linked in,
-plugin/hybrid/), and their output images compared.  usage: python tools/run_reference_tests.py [--out gpurun_out/reference_tests.json]"""
+and once with `b200` (the same backend with this repository's BVH builder, host layer, device-library traversal and native
+kernel launch linked in, plugin/hybrid/) — plus `b200o` when built (the same, but kernels still launched through OptiX: the
+developer variant of plugin/hybrid/build.sh) — and their output images compared.  usage: python tools/run_reference_tests.py [--out gpurun_out/reference_tests.json]"""
 import argparse
 import json
 import os
@@ -69,7 +70,8 @@ def main():
             res[test] = {"unavailable": "not built"}
             continue
         imgs, entry = {}, {}
-        for backend in ("cuda", "b200"):
+        backends = ("cuda", "b200") + (("b200o",) if os.path.exists(os.path.join(BIN, "liblc-backend-b200o.so")) else ())
+        for backend in backends:
             d = os.path.join("/tmp", f"lc_{test}_{backend}")
             os.makedirs(d, exist_ok=True)
             t0 = time.time()
@@ -85,9 +87,10 @@ def main():
                 subprocess.run(["cp", png, os.path.join(ROOT, "gpurun_out", f"{test}_{backend}.png")])
             else:
                 entry[backend]["log_tail"] = (r.stdout + r.stderr)[-600:]
-        if len(imgs) == 2:
-            diff = np.abs(imgs["cuda"] - imgs["b200"])
-            entry["image"] = {"shape": list(imgs["cuda"].shape), "max_abs_diff": int(diff.max()), "mean_abs_diff": float(diff.mean()),
+        for other, key in (("b200", "image"), ("b200o", "image_optix_launch")):
+            if "cuda" in imgs and other in imgs:
+                diff = np.abs(imgs["cuda"] - imgs[other])
+                entry[key] = {"shape": list(imgs["cuda"].shape), "max_abs_diff": int(diff.max()), "mean_abs_diff": float(diff.mean()),
                               "pixels_differing_by_more_than_2": int((diff.max(axis=2) > 2).sum()),
                               "nonblack_pixels": int((imgs["cuda"][:, :, :3].sum(axis=2) > 0).sum())}
         res[test] = entry
