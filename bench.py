@@ -567,18 +567,19 @@ def main():
 
     # ------------------------------------------------------------------ e2e: host buffers through the public call
     e2e = None
+    e2e_chunk = int(os.environ.get("LCB_E2E_CHUNK", str(1 << 19)))
     if not args.no_e2e:
         h_rays = torch.empty(2 * n * 32, dtype=torch.uint8).pin_memory()
         h_rays[:n * 32] = torch.from_numpy(primary.view(np.uint8).reshape(-1))
         h_rays[n * 32:] = torch.from_numpy(bounce.view(np.uint8).reshape(-1))
         h_hits = torch.empty((2 * n, 6), dtype=torch.int32).pin_memory()
         for _ in range(2):
-            acc.trace_closest_host(h_rays, h_hits, chunk_rays=1 << 19)
+            acc.trace_closest_host(h_rays, h_hits, chunk_rays=e2e_chunk)
         barrier()
         t0 = time.perf_counter()
         reps = max(3, min(K, 10))
         for _ in range(reps):
-            acc.trace_closest_host(h_rays, h_hits, chunk_rays=1 << 19)
+            acc.trace_closest_host(h_rays, h_hits, chunk_rays=e2e_chunk)
         barrier()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -587,7 +588,37 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * reps * 2 * n / dt / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 2 * n * 32, "d2h_bytes_per_step": 2 * n * 24,
                "ms_per_step": dt / reps * 1e3, "api": "Accel.trace_closest_host -> lcbTraceClosestHost (pinned host rays in, pinned host hits out, "
-               "512Ki-ray chunks, four in flight on four streams)"}
+               f"{e2e_chunk >> 10}Ki-ray chunks, four in flight on four streams)"}
+        # the ceiling of that path on THIS box: the same bytes (rays in, hits out) moved by plain copies on two streams, all ranks
+        # at once, nothing traced — what host<->device bandwidth alone allows
+        d_stage_in = torch.empty(2 * n * 32, dtype=torch.uint8, device=tdev)
+        d_stage_out = torch.empty((2 * n, 6), dtype=torch.int32, device=tdev)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        ck = (1 << 19) * 32
+        best = 1e30
+        for _ in range(3):
+            barrier()
+            t0 = time.perf_counter()
+            for off in range(0, 2 * n * 32, ck):
+                with torch.cuda.stream(s_in):
+                    d_stage_in[off:off + ck].copy_(h_rays[off:off + ck], non_blocking=True)
+                r0 = off // 32
+                with torch.cuda.stream(s_out):
+                    h_hits[r0:r0 + (1 << 19)].copy_(d_stage_out[r0:r0 + (1 << 19)], non_blocking=True)
+            s_in.synchronize(), s_out.synchronize()
+            barrier()
+            best = min(best, time.perf_counter() - t0)
+        if world > 1:
+            t = torch.tensor([best], dtype=torch.float64, device=tdev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t.item())
+        e2e["copy_only_ms_per_step"] = best * 1e3
+        e2e["copy_only_mrays_s"] = world * 2 * n / best / 1e6
+        e2e["copy_only_gbs_aggregate"] = world * 2 * n * 56 / best / 1e9
+        e2e["fraction_of_copy_ceiling"] = e2e["value"] / e2e["copy_only_mrays_s"]
+        del d_stage_in, d_stage_out
+        # restore what the ceiling probe overwrote, through the real path
+        acc.trace_closest_host(h_rays, h_hits, chunk_rays=e2e_chunk)
         # the host path must return exactly what the resident path returned
         assert torch.equal(h_hits[:n], d_hits_p.cpu()) and torch.equal(h_hits[n:], d_hits_b.cpu())
 

@@ -97,6 +97,8 @@ LCRT_API int lcrtRefitAabbs(lcrtStream stream, const void *aabbs, uint32_t aabb_
 /* instance buffer (80-byte records) maintenance */
 LCRT_API int lcrtInstancesInit(lcrtStream stream, void *instances, uint32_t first, uint32_t count);
 LCRT_API int lcrtInstancesApplyMods(lcrtStream stream, void *instances, const void *mods_device, uint32_t mod_count);
+/* the same for at most 16 modifications in HOST memory: they travel in the kernel's launch parameters, no staging copy */
+LCRT_API int lcrtInstancesApplyModsHost(lcrtStream stream, void *instances, const void *mods_host, uint32_t mod_count);
 LCRT_API int lcrtInstancesUpdateHandles(lcrtStream stream, void *instances, const void *updates_device, uint32_t count);
 
 LCRT_API int lcrtBuildTlas(lcrtStream stream, const void *instances, uint32_t instance_count, uint32_t flags, void *temp,

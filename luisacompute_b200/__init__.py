@@ -84,7 +84,7 @@ class Sizes(C.Structure):
 ABI_SYMBOLS = [
     "lcrtGetVersion", "lcrtGetErrorString", "lcrtGetLastCudaError", "lcrtAccelComputeMemoryUsage", "lcrtBuildTriangles",
     "lcrtRefitTriangles", "lcrtBuildAabbs", "lcrtRefitAabbs", "lcrtInstancesInit", "lcrtInstancesApplyMods",
-    "lcrtInstancesUpdateHandles", "lcrtBuildTlas", "lcrtRefitTlas", "lcrtTraceClosest", "lcrtTraceAny", "lcrtQuery",
+    "lcrtInstancesApplyModsHost", "lcrtInstancesUpdateHandles", "lcrtBuildTlas", "lcrtRefitTlas", "lcrtTraceClosest", "lcrtTraceAny", "lcrtQuery",
     "lcrtBlobGetInfo", "lcrtDeviceLibrarySource", "lcrtSortTempBytes", "lcrtSortPairs",
     "lcbDeviceCreate", "lcbDeviceDestroy", "lcbBackendName", "lcbCreateMesh", "lcbDestroyMesh", "lcbCreateProceduralPrimitive",
     "lcbDestroyProceduralPrimitive", "lcbCreateAccel", "lcbDestroyAccel", "lcbMeshBuild", "lcbProceduralPrimitiveBuild",
@@ -118,6 +118,7 @@ def lib():
     L.lcrtRefitAabbs.argtypes = [vp, vp, u32, vp, u64, vp]
     L.lcrtInstancesInit.argtypes = [vp, vp, u32, u32]
     L.lcrtInstancesApplyMods.argtypes = [vp, vp, vp, u32]
+    L.lcrtInstancesApplyModsHost.argtypes = [vp, vp, vp, u32]
     L.lcrtInstancesUpdateHandles.argtypes = [vp, vp, vp, u32]
     L.lcrtBuildTlas.argtypes = [vp, vp, u32, u32, vp, u64, vp, u64]
     L.lcrtRefitTlas.argtypes = [vp, vp, u32, vp, u64, vp]

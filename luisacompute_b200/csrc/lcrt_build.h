@@ -20,6 +20,23 @@ __device__ __forceinline__ uint32_t lcrt_atomic_add_acq_rel(uint32_t *p, uint32_
     return old;
 }
 #define LCRT_ATOMIC_ADD_ACQ_REL(p, v) lcrt_atomic_add_acq_rel((p), (v))
+// atomicAdd on a counter that every thread of the grid hits: the lanes that arrive together add up first and send ONE atomic
+// (same-address atomics are served one at a time by a single L2 slice)
+__device__ __forceinline__ uint32_t lcrt_atomic_add_aggregated(uint32_t *p, uint32_t v) {
+    const uint32_t m = __activemask(), lane = threadIdx.x & 31u;
+    uint32_t before = 0u, total = 0u;
+    for (uint32_t mm = m; mm; mm &= mm - 1u) {
+        const int b = __ffs((int)mm) - 1;
+        const uint32_t x = __shfl_sync(m, v, b);
+        before += (uint32_t)b < lane ? x : 0u;
+        total += x;
+    }
+    const int leader = __ffs((int)m) - 1;
+    uint32_t base = 0u;
+    if ((int)lane == leader) base = atomicAdd(p, total);
+    return __shfl_sync(m, base, leader) + before;
+}
+#define LCRT_ATOMIC_ADD_AGG(p, v) lcrt_atomic_add_aggregated((p), (v))
 #define LCRT_VOLATILE_LOAD_U32(p) (*reinterpret_cast<const volatile uint32_t *>(p))
 // data produced by other SMs inside the same kernel must not be served from this SM's (non-coherent) L1
 #define LCRT_LOAD_CG_F4(p) __ldcg(reinterpret_cast<const float4 *>(p))
@@ -31,6 +48,7 @@ inline uint32_t host_atomic_add(uint32_t *p, uint32_t v) {
 }
 #define LCRT_ATOMIC_ADD(p, v) ::lcrt::host_atomic_add((p), (v))
 #define LCRT_ATOMIC_ADD_ACQ_REL(p, v) ::lcrt::host_atomic_add((p), (v))
+#define LCRT_ATOMIC_ADD_AGG(p, v) ::lcrt::host_atomic_add((p), (v))
 #define LCRT_FENCE() ((void)0)
 #define LCRT_VOLATILE_LOAD_U32(p) (*(p))
 #define LCRT_LOAD_CG_F4(p) (*(p))
@@ -279,13 +297,29 @@ LCRT_HD Bvh2Half load_half_cg(const Bvh2Half *src) {// written by another SM ins
     return h;
 }
 
-// one thread per leaf (Apetrei 2014): climbs while it is the second child to arrive
-LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
-    const uint32_t n = t.n;
-    uint32_t left = i, right = i;
+// merges the sibling half `s` into `h` (which becomes the description of their parent `parent`)
+LCRT_HD void merge_halves(const Bvh2 &t, Bvh2Half &h, const Bvh2Half &s, uint32_t parent, uint32_t left, uint32_t right) {
+    for (int a = 0; a < 3; a++) h.lo[a] = fminf(h.lo[a], s.lo[a]), h.hi[a] = fmaxf(h.hi[a], s.hi[a]);
+    const uint32_t count = (h.count_mark & ~LEAF_MARK) + (s.count_mark & ~LEAF_MARK);
+    const float area = area_of(h.lo, h.hi);
+    const float c_split = t.ci * area + h.cost + s.cost;
+    const float c_leaf = area * (float)count;
+    if (count <= t.max_leaf && c_leaf <= c_split) h.cost = c_leaf, h.count_mark = count | LEAF_MARK, h.slots = 1u;
+    else h.cost = c_split, h.count_mark = count, h.slots = h.slots + s.slots;
+    h.id = parent, h.first = left, h.last = right;
+}
+
+LCRT_HD Bvh2Half leaf_half(uint32_t n, uint32_t i, const Box &leaf_box) {
     Bvh2Half h;
     for (int a = 0; a < 3; a++) h.lo[a] = leaf_box.lo[a], h.hi[a] = leaf_box.hi[a];
     h.cost = area_of(h.lo, h.hi), h.count_mark = 1u | LEAF_MARK, h.id = (n - 1u) + i, h.slots = 1u, h.first = i, h.last = i;
+    return h;
+}
+
+// Apetrei 2014: a thread that holds the finished subtree [left, right] (described by `h`) climbs while it is the second child
+// to arrive at the parent; the halves and the arrival counters live in global memory.
+LCRT_HD void lbvh_climb_from(const Bvh2 &t, uint32_t left, uint32_t right, Bvh2Half h) {
+    const uint32_t n = t.n;
     for (;;) {
         if (left == 0u && right == n - 1u) {
             store_half(t.root, h);
@@ -301,16 +335,12 @@ LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) {
         const Bvh2Half s = load_half_cg(from_left ? &t.node[parent].r : &t.node[parent].l);
         if (from_left) right = s.last;
         else left = s.first;
-        for (int a = 0; a < 3; a++) h.lo[a] = fminf(h.lo[a], s.lo[a]), h.hi[a] = fmaxf(h.hi[a], s.hi[a]);
-        const uint32_t count = (h.count_mark & ~LEAF_MARK) + (s.count_mark & ~LEAF_MARK);
-        const float area = area_of(h.lo, h.hi);
-        const float c_split = t.ci * area + h.cost + s.cost;
-        const float c_leaf = area * (float)count;
-        if (count <= t.max_leaf && c_leaf <= c_split) h.cost = c_leaf, h.count_mark = count | LEAF_MARK, h.slots = 1u;
-        else h.cost = c_split, h.count_mark = count, h.slots = h.slots + s.slots;
-        h.id = parent, h.first = left, h.last = right;
+        merge_halves(t, h, s, parent, left, right);
     }
 }
+
+// one thread per leaf
+LCRT_HD void lbvh_climb(const Bvh2 &t, uint32_t i, const Box &leaf_box) { lbvh_climb_from(t, i, i, leaf_half(t.n, i, leaf_box)); }
 
 // ------------------------------------------------------------------------------------------ BVH8 emission
 struct Bvh8Out {
@@ -516,7 +546,7 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
         else n_int++;
     }
     const uint32_t child_base = n_int ? LCRT_ATOMIC_ADD(&o.counters[0 * COUNTER_STRIDE], n_int) : 0u;
-    const uint32_t prim_base = n_prims ? LCRT_ATOMIC_ADD(&o.counters[1 * COUNTER_STRIDE], n_prims) : 0u;
+    const uint32_t prim_base = n_prims ? LCRT_ATOMIC_ADD_AGG(&o.counters[1 * COUNTER_STRIDE], n_prims) : 0u;
     if (n_int && child_base + n_int > o.node_capacity) {
         o.header->error = 1u;
         return false;
@@ -554,9 +584,7 @@ LCRT_HD_NOINLINE bool collapse_node(const Bvh2 &t, const Bvh8Out &o, const Input
         for (int a = 0; a < 3; a++) o.header->lo[a] = nb.lo[a], o.header->hi[a] = nb.hi[a];
         if (o.parent) o.parent[0] = INVALID_U32;
     }
-    // tasks and parents are released before the completion counter moves
-    if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], n_prims);
-    else LCRT_FENCE();
+    if (n_prims) LCRT_ATOMIC_ADD_AGG(&o.counters[2 * COUNTER_STRIDE], n_prims);
     return true;
 }
 

@@ -27,6 +27,7 @@
 #include "lcrt_traverse.h"
 
 #if defined(LCRT_DEVLIB_STANDALONE)
+#include <stdio.h>
 // ---- minimal prelude: only what the RT section needs from cuda_device_math.h / cuda_device_resource.h
 using lc_uint = unsigned int;
 using lc_ulong = unsigned long long;
@@ -152,6 +153,36 @@ __device__ inline void lc_accel_set_instance_opacity(LCAccel accel, lc_uint inde
     }
 }
 __device__ inline void lc_accel_set_instance_user_id(LCAccel accel, lc_uint index, lc_uint user_id) noexcept { accel.instances[index].user_id = user_id; }
+
+// ------------------------------------------------------------------------------------------ motion instances (not supported)
+// The code generator lowers the DSL's motion-instance accessors to these names (cuda_codegen_ast.cpp:1047-1050; the reference's own
+// library spells them lc_instance_motion_* at this commit, cuda_device_resource.h:1387-1448, so such a kernel does not even compile
+// there).  Motion blur is outside this backend's scope: the names resolve, and a kernel that reaches one of them
+// stops with a message instead of failing inside NVRTC.
+namespace lcrt {
+__device__ inline void devlib_motion_unsupported() noexcept {
+    printf("[lc-backend-b200] motion-blur instances are not supported by this backend (SURVEY.md 8 f4)\n");
+    __trap();
+}
+struct DevlibAnyValue {// converts to whatever record type the generated code expects (LCMotionSRT is emitted after this library)
+    template<class T>
+    __device__ operator T() const noexcept {
+        T t{};
+        return t;
+    }
+};
+}// namespace lcrt
+[[nodiscard]] __device__ inline lc_float4x4 lc_accel_instance_motion_matrix(LCAccel, lc_uint, lc_uint) noexcept {
+    lcrt::devlib_motion_unsupported();
+    return lc_make_float4x4(1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f, 1.f);
+}
+[[nodiscard]] __device__ inline lcrt::DevlibAnyValue lc_accel_instance_motion_srt(LCAccel, lc_uint, lc_uint) noexcept {
+    lcrt::devlib_motion_unsupported();
+    return {};
+}
+__device__ inline void lc_accel_set_instance_motion_matrix(LCAccel, lc_uint, lc_uint, lc_float4x4) noexcept { lcrt::devlib_motion_unsupported(); }
+template<class SRT>
+__device__ inline void lc_accel_set_instance_motion_srt(LCAccel, lc_uint, lc_uint, SRT) noexcept { lcrt::devlib_motion_unsupported(); }
 
 // ------------------------------------------------------------------------------------------ intersect / intersect_any
 namespace lcrt {
@@ -349,8 +380,15 @@ struct DevlibQueryCallbacks {
 // run time, as the reference's __intersection__ / __anyhit__ programs do): a path tracer with a query_all and a query_any
 // site is 57 KB of SASS with a traversal per site, beyond the 32 KB L1.5 instruction cache, and spent 56 % of its
 // issue slots waiting for instructions.  LCRT_RAY_QUERY_INLINE=1 restores one specialised traversal per site.
+// A kernel with a single RayQuery site has nothing to share: there the traversal is inlined into the site, which also lets the
+// compiler keep the handlers' capture struct (`LCRayQueryCtx`, cuda_codegen_ast.cpp:446-521) in registers instead of
+// round-tripping it through local memory behind the `void *ctx` of an out-of-line call.
 #ifndef LCRT_RAY_QUERY_INLINE
+#if LUISA_RAY_QUERY_IMPL_COUNT <= 1
+#define LCRT_RAY_QUERY_INLINE 1
+#else
 #define LCRT_RAY_QUERY_INLINE 0
+#endif
 #endif
 #if LCRT_RAY_QUERY_INLINE
 __device__ inline

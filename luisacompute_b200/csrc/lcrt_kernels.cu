@@ -35,9 +35,10 @@ enum SmallSlots : uint32_t {
     SM_ROOT_HALF = 32 /* Bvh2Half of the root (12 words, 16-byte aligned) */,
     // the words every wide node touches, each on its own 128-byte line (they are served by one L2 slice each; sharing a
     // line with the polled flags made the counters' atomics queue behind the polls)
-    SM_COUNTERS = 64 /* nodes, prims, done prims at COUNTER_STRIDE words */, SM_DONE = 160 /* every primitive has its record slot */, SM_ABORT = 192
+    SM_COUNTERS = 64 /* nodes, prims, done prims at COUNTER_STRIDE words */, SM_DONE = 160 /* every wide node that is not deferred has been built */, SM_ABORT = 192,
+    SM_PENDING = 224 /* scheduled, not yet built wide nodes of the octet kernel */
 };
-static_assert(SM_COUNTERS + 2 * COUNTER_STRIDE < SM_DONE && SM_ABORT < SMALL_WORDS, "scratch words");
+static_assert(SM_COUNTERS + 2 * COUNTER_STRIDE < SM_DONE && SM_PENDING < SMALL_WORDS, "scratch words");
 static_assert(SM_ROOT_HALF * 4 % 16 == 0 && SM_ROOT_HALF + sizeof(Bvh2Half) / 4 <= SMALL_WORDS, "scratch words");
 
 __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t flags, BlobLayout L, uint32_t *small) {
@@ -54,6 +55,7 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
         *h = hd;
         small[SM_CMIN + 0] = small[SM_CMIN + 1] = small[SM_CMIN + 2] = 0xffffffffu;
         small[SM_COUNTERS + 0 * COUNTER_STRIDE] = 1u;// the root
+        small[SM_PENDING] = 1u;
         if (n == 0u) {
             // an empty structure: one node with no children; nothing can be hit
             Node8 nd;
@@ -135,16 +137,105 @@ __global__ void __launch_bounds__(256) k_morton(const f4 *__restrict__ pbox, uin
     if (i < n) keys[i] = (morton63(box_from_pbox(pbox[2ull * i], pbox[2ull * i + 1]), clo, inv_ext, bits) << index_bits) | (uint64_t)i;
 }
 
-__global__ void __launch_bounds__(64) k_climb(Bvh2 t, const f4 *__restrict__ pbox) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < t.n) {
-        const uint32_t p = t.order(i);
-        lbvh_climb(t, i, box_from_pbox(pbox[2ull * p], pbox[2ull * p + 1]));
+// The climb, block-local: a block owns CLIMB_CHUNK consecutive sorted leaves and keeps every binary node whose whole range
+// lies inside that chunk (99 % of them at any size) in SHARED memory — halves, arrival counters, shared-memory atomics — and
+// the thread that completes such a node writes its finished 96-byte record to global memory once.  Only nodes whose range
+// crosses a chunk boundary go through global memory and global atomics (lbvh_climb_from).  Which is which is decided
+// from the split levels alone (level(j) = highest bit in which sorted keys j and j + 1 differ; +inf outside the array):
+// node p, the split between leaves p and p + 1, spans the maximal interval around p whose other levels are smaller, so a
+// thread arriving from the left asks whether a larger level exists to the right of p inside the chunk (suffix maxima), one
+// arriving from the right whether one exists to the left (prefix maxima); both answers agree on "inside".
+constexpr int CLIMB_CHUNK = 256;
+struct ClimbSmem {
+    Bvh2Half l[CLIMB_CHUNK], r[CLIMB_CHUNK];// halves of node b0 + k
+    uint32_t flag[CLIMB_CHUNK];
+    uint8_t level[CLIMB_CHUNK + 1], premax[CLIMB_CHUNK + 1], sufmax[CLIMB_CHUNK + 1];// index k <-> split j = b0 - 1 + k
+};
+__global__ void __launch_bounds__(CLIMB_CHUNK) k_climb(Bvh2 t, const f4 *__restrict__ pbox) {
+    __shared__ ClimbSmem sm;
+    const uint32_t n = t.n, tid = threadIdx.x;
+    const uint32_t b0 = blockIdx.x * CLIMB_CHUNK, b1 = b0 + CLIMB_CHUNK < n ? b0 + CLIMB_CHUNK : n;// leaves [b0, b1)
+    // ---- split levels of j = b0 - 1 .. b1 - 1 (255 = outside the array), their prefix / suffix maxima
+    for (uint32_t k = tid; k <= (uint32_t)CLIMB_CHUNK; k += CLIMB_CHUNK) {
+        const long long j = (long long)b0 - 1 + k;
+        uint32_t lv = 255u;
+        if (j >= 0 && j + 1 < (long long)n && j <= (long long)b1 - 1) lv = 63u - (uint32_t)__clzll((long long)(t.keys[j] ^ t.keys[j + 1]));
+        if (j > (long long)b1 - 1) lv = 0u;// beyond this chunk's last split: not part of the maxima
+        sm.level[k] = (uint8_t)lv;
     }
+    sm.flag[tid] = 0u;
+    __syncthreads();
+    if (tid < 32u) {
+        // 257 bytes: one warp, eight (nine) per lane, then a shuffle scan — twice (prefix, suffix)
+        const uint32_t cnt = b1 - b0 + 1u;// valid entries: k = 0 .. b1 - b0
+        uint32_t run = 0u;
+        const uint32_t per = (CLIMB_CHUNK + 1 + 31) / 32, k0 = tid * per;
+        for (uint32_t k = k0; k < k0 + per && k < cnt; k++) run = run > sm.level[k] ? run : sm.level[k];
+        uint32_t inc = run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (tid >= (uint32_t)o) inc = inc > v ? inc : v;
+        }
+        uint32_t carry = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (tid == 0u) carry = 0u;
+        for (uint32_t k = k0; k < k0 + per && k < cnt; k++) {
+            carry = carry > sm.level[k] ? carry : sm.level[k];
+            sm.premax[k] = (uint8_t)carry;
+        }
+        run = 0u;
+        for (uint32_t k = k0; k < k0 + per && k < cnt; k++) run = run > sm.level[k] ? run : sm.level[k];
+        inc = run;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_down_sync(0xffffffffu, inc, o);
+            if (tid + (uint32_t)o < 32u) inc = inc > v ? inc : v;
+        }
+        carry = __shfl_down_sync(0xffffffffu, inc, 1);
+        if (tid == 31u) carry = 0u;
+        for (uint32_t kk = 0; kk < per; kk++) {
+            const uint32_t k = k0 + per - 1u - kk;
+            if (k >= cnt) continue;
+            carry = carry > sm.level[k] ? carry : sm.level[k];
+            sm.sufmax[k] = (uint8_t)carry;
+        }
+    }
+    __syncthreads();
+    const uint32_t i = b0 + tid;
+    if (i >= n) return;
+    uint32_t left = i, right = i;
+    const uint32_t prim = t.order(i);
+    Bvh2Half h = leaf_half(n, i, box_from_pbox(pbox[2ull * prim], pbox[2ull * prim + 1]));
+    for (;;) {
+        if (left == 0u && right == n - 1u) {
+            store_half(t.root, h);
+            return;
+        }
+        // the two candidate parents are splits right and left - 1, both inside this chunk's level table
+        const uint32_t lr = sm.level[right - b0 + 1u], ll = sm.level[left - b0];
+        const bool from_left = left == 0u || (right != n - 1u && lr < ll);
+        const uint32_t p = from_left ? right : left - 1u;
+        const uint32_t k = p - b0 + 1u;// index of split p in the tables (p >= b0 - 1)
+        bool local = p >= b0 && p + 1u <= b1 - 1u;
+        if (local) local = from_left ? sm.sufmax[k + 1u] > sm.level[k] : sm.premax[k - 1u] > sm.level[k];
+        if (!local) break;// this node's range crosses the chunk: global memory from here on
+        const uint32_t q = p - b0;
+        copy_vec16(from_left ? &sm.l[q] : &sm.r[q], &h, 3);
+        __threadfence_block();
+        if (atomicAdd(&sm.flag[q], 1u) == 0u) return;// the sibling (a thread of this block) will finish this node
+        __threadfence_block();
+        Bvh2Half s;
+        copy_vec16(&s, from_left ? &sm.r[q] : &sm.l[q], 3);
+        // the finished record goes out once: both halves
+        store_half(from_left ? &t.node[p].l : &t.node[p].r, h);
+        store_half(from_left ? &t.node[p].r : &t.node[p].l, s);
+        if (from_left) right = s.last;
+        else left = s.first;
+        merge_halves(t, h, s, p, left, right);
+    }
+    lbvh_climb_from(t, left, right, h);
 }
 
 #ifndef LCRT_COLLAPSE_MIN_BLOCKS
-#define LCRT_COLLAPSE_MIN_BLOCKS 6
+#define LCRT_COLLAPSE_MIN_BLOCKS 8
 #endif
 constexpr int COLLAPSE_BLOCK = 128;
 
@@ -161,10 +252,13 @@ struct OctChild {
     bool valid, leaf;
     uint32_t slots, count, first;// leaf slots below the child; primitives in it and their first sorted position if it is a leaf
 };
+// NC: the binary hierarchy was written by an EARLIER kernel (read-only path); the single-block small build reads what it
+// wrote itself a moment ago and uses ordinary loads
+template<bool NC>
 __device__ __forceinline__ void oct_set(OctChild &c, const Bvh2Half *src) {
     const float4 *s = reinterpret_cast<const float4 *>(src);
-    const float4 a = __ldg(s), b = __ldg(s + 1);
-    const uint4 m = __ldg(reinterpret_cast<const uint4 *>(s + 2));
+    const float4 a = NC ? __ldg(s) : s[0], b = NC ? __ldg(s + 1) : s[1];
+    const uint4 m = NC ? __ldg(reinterpret_cast<const uint4 *>(s + 2)) : *reinterpret_cast<const uint4 *>(s + 2);
     c.valid = true;
     c.lox = a.x, c.loy = a.y, c.loz = a.z, c.hix = b.x, c.hiy = b.y, c.hiz = b.z;
     const float dx = b.x - a.x, dy = b.y - a.y, dz = b.z - a.z;
@@ -174,11 +268,21 @@ __device__ __forceinline__ void oct_set(OctChild &c, const Bvh2Half *src) {
     c.count = cm & ~LEAF_MARK;
     c.id = m.x, c.slots = m.y, c.first = m.z;
 }
+// the record an opening of this child would read: asked for early, it is in L1 when the (sequential) opening loop gets there
+__device__ __forceinline__ void oct_prefetch(const Bvh2 &t, const OctChild &c) {
+    if (c.valid && !c.leaf) {
+        const char *p = reinterpret_cast<const char *>(&t.node[c.id]);
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
+    }
+}
 // opens child `k` of every octet with `go`: its left child stays in lane k, its right child goes to lane nc
+template<bool NC>
 __device__ __forceinline__ void oct_open(const Bvh2 &t, OctChild &c, uint32_t l, bool go, uint32_t k, uint32_t &nc) {
     const uint32_t id = __shfl_sync(0xffffffffu, c.id, (int)k, 8);
-    if (go && l == k) oct_set(c, &t.node[id].l);
-    if (go && l == nc) oct_set(c, &t.node[id].r);
+    if (go && l == k) oct_set<NC>(c, &t.node[id].l);
+    if (go && l == nc) oct_set<NC>(c, &t.node[id].r);
+    if (go && (l == k || l == nc)) oct_prefetch(t, c);
     if (go) nc++;
 }
 // arg-max over the octet of an integer key (0 = "not a candidate"); ties go to the lower lane; returns 8 if there is no
@@ -189,9 +293,14 @@ __device__ __forceinline__ uint32_t oct_argmax(uint32_t key, uint32_t l, uint32_
 }
 __device__ __forceinline__ uint32_t oct_or(uint32_t v, uint32_t omask) { return __reduce_or_sync(omask, v); }
 
-template<class Input>
+constexpr uint32_t TASK_FITS = 0x80000000u;// task word y: the node's whole subtree fits into it (all children leaves): built by k_collapse_fits
+
+// SPLIT: children whose subtree fits into one node are only scheduled (flagged TASK_FITS) and left to k_collapse_fits, one
+// thread per node, after this kernel; `pending` counts the scheduled, not yet built nodes that are NOT deferred, and the
+// octet that brings it to zero raises `done`.
+template<class Input, bool NC, bool SPLIT>
 __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid, uint32_t depth, bool act,
-                               unsigned char *node_smem, uint32_t *done_flag) {
+                               unsigned char *node_smem, uint32_t *done_flag, uint32_t *pending) {
     const uint32_t l = threadIdx.x & 7u;
     OctChild c;
     c.id = INVALID_U32, c.valid = false, c.leaf = true, c.slots = 0u, c.count = 0u, c.first = 0u, c.area = 0.f;
@@ -202,15 +311,16 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
         const uint32_t cm = t.root->count_mark;
         if (cm & LEAF_MARK) {
             nc = 1u;
-            if (l == 0u) oct_set(c, t.root);
+            if (l == 0u) oct_set<NC>(c, t.root);
         } else {
             bid = t.root->id;
         }
     }
     if (act && nc == 0u) {
         nc = 2u;
-        if (l == 0u) oct_set(c, &t.node[bid].l);
-        if (l == 1u) oct_set(c, &t.node[bid].r);
+        if (l == 0u) oct_set<NC>(c, &t.node[bid].l);
+        if (l == 1u) oct_set<NC>(c, &t.node[bid].r);
+        if (l < 2u) oct_prefetch(t, c);
     }
     const uint32_t omask = 0xffu << (threadIdx.x & 24u), oshift = threadIdx.x & 24u;
     // a subtree that fits into one node entirely (six wide nodes out of seven) is dissolved level by level, every
@@ -224,8 +334,8 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             // lane k (opening) keeps the left half; lane nc + r takes the right half of the r-th opening lane
             const int src = (l >= nc && l - nc < (uint32_t)__popc(om)) ? (int)__fns(om, 0u, (int)(l - nc) + 1) : (int)l;
             const uint32_t id = __shfl_sync(0xffffffffu, c.id, src, 8);
-            if (opening) oct_set(c, &t.node[id].l);
-            else if (om && l >= nc && l - nc < (uint32_t)__popc(om)) oct_set(c, &t.node[id].r);
+            if (opening) oct_set<NC>(c, &t.node[id].l);
+            else if (om && l >= nc && l - nc < (uint32_t)__popc(om)) oct_set<NC>(c, &t.node[id].r);
             nc += (uint32_t)__popc(om);
         }
     }
@@ -236,7 +346,7 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             const bool cand = gen && nc < 8u && c.valid && !c.leaf && c.slots > 8u;
             const uint32_t best = oct_argmax(cand ? __float_as_uint(c.area) + 1u : 0u, l, omask);
             if (!__any_sync(0xffffffffu, best < 8u)) break;
-            oct_open(t, c, l, best < 8u, best & 7u, nc);
+            oct_open<NC>(t, c, l, best < 8u, best & 7u, nc);
         }
         // ---- dissolve, smallest first, children whose whole subtree fits into the free slots
         uint32_t pending = 0u;
@@ -253,7 +363,7 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             pending &= ~(1u << k);
             const bool kleaf = __shfl_sync(0xffffffffu, (int)c.leaf, (int)k, 8) != 0;
             const bool go = more && !kleaf;
-            oct_open(t, c, l, go, k, nc);
+            oct_open<NC>(t, c, l, go, k, nc);
             if (go) pending |= (1u << k) | (1u << (nc - 1u));
         }
     }
@@ -336,8 +446,9 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             const uint32_t w = child_base + (uint32_t)__popc(int_by_slot & ((1u << slot) - 1u));
             meta = (uint8_t)((1u << 5) | (24u + (uint32_t)slot));
             if (o.parent) o.parent[w] = (widx << 3) | (uint32_t)slot;
-            // one 64-bit store: a consumer that sees the node id also sees the depth
-            __stcg(reinterpret_cast<unsigned long long *>(&o.task[w]), ((unsigned long long)(depth + 1u) << 32) | c.id);
+            // one 64-bit store: a consumer that sees the node id also sees the depth (and whether the node is deferred)
+            const uint32_t fits = (SPLIT && c.slots <= 8u) ? TASK_FITS : 0u;
+            __stcg(reinterpret_cast<unsigned long long *>(&o.task[w]), ((unsigned long long)((depth + 1u) | fits) << 32) | c.id);
         } else {
             const uint32_t below = cnt_by_slot & ((1u << (2 * slot)) - 1u);
             const uint32_t po = (uint32_t)__popc(below & 0x5555u) + 2u * (uint32_t)__popc(below & 0xaaaau);
@@ -365,10 +476,18 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             o.header->hi[0] = nhx, o.header->hi[1] = nhy, o.header->hi[2] = nhz;
             if (o.parent) o.parent[0] = INVALID_U32;
         }
-        if (n_prims && LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], n_prims) + n_prims == t.n) {
-            // the last primitive has its slot: every wide node has been processed
+        if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], n_prims);
+    }
+    if constexpr (SPLIT) {
+        // this node is built; its children that are not deferred are now pending (their tasks were written above)
+        const uint32_t upper = oct_or((is_int && c.slots > 8u) ? (1u << l) : 0u, omask);
+        if (act && l == 0u) {
+            const uint32_t add = (uint32_t)__popc(upper);
             __threadfence();
-            *reinterpret_cast<volatile uint32_t *>(done_flag) = 1u;
+            if (atomicAdd(pending, add - 1u) + add - 1u == 0u) {
+                __threadfence();
+                *reinterpret_cast<volatile uint32_t *>(done_flag) = 1u;
+            }
         }
     }
     __syncwarp();
@@ -383,7 +502,7 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
 // never scheduled leave then.  (Round 1 ran level by level with a grid barrier per level: 0.58 ms at 1.3 M triangles.)
 template<class Input>
 __global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *done_flag,
-                                                                                        uint32_t *levels_out) {
+                                                                                        uint32_t *levels_out, uint32_t *pending) {
     __shared__ __align__(16) unsigned char node_smem[(COLLAPSE_BLOCK / 8) * sizeof(Node8)];
     __shared__ uint32_t s_depth;
     if (threadIdx.x == 0) s_depth = 0u;
@@ -429,20 +548,178 @@ __global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_co
                     break;
                 }
             }
-            __nanosleep(idle < 16u ? 32u : 200u);
+            __nanosleep(idle < 8u ? 40u : idle < 32u ? 160u : idle < 128u ? 640u : 2000u);// back off: idle polls cost the busy warps issue slots
         }
         if (__all_sync(0xffffffffu, finished)) break;
         word = __shfl_sync(0xffffffffu, word, (int)(threadIdx.x & 24u));
-        const uint32_t bid = (uint32_t)word, depth = (uint32_t)(word >> 32);
-        if (!collapse_octet(t, o, in, w, bid, depth, act, node_smem, done_flag)) atomicExch(abort_flag, 1u);
+        const uint32_t bid = (uint32_t)word, depth = (uint32_t)(word >> 32) & ~TASK_FITS;
+        const bool deferred = act && ((uint32_t)(word >> 32) & TASK_FITS) != 0u && w != 0u;// k_collapse_fits builds it
+        const bool build = act && !deferred;
+        if (__any_sync(0xffffffffu, build)) {
+            if (!collapse_octet<Input, true, true>(t, o, in, w, bid, depth, build, node_smem, done_flag, pending)) atomicExch(abort_flag, 1u);
+        }
         if (act) {
-            if (l == 0u) atomicMax(&s_depth, depth);
+            if (l == 0u && build) atomicMax(&s_depth, depth);
             w += stride;
             if (w >= o.node_capacity) finished = true;
         }
     }
     __syncthreads();
     if (threadIdx.x == 0 && s_depth) atomicMax(levels_out, s_depth);
+}
+
+// The deferred nodes (six out of seven): a subtree of at most eight leaf slots becomes one wide node whose children are all
+// leaves.  Nothing depends on them, so they are built after the octet kernel, ONE THREAD PER NODE over the whole index range
+// (collapse_node, the serial statement of the same decisions), with every SM full.
+template<class Input>
+__global__ void __launch_bounds__(128) k_collapse_fits(Bvh2 t, Bvh8Out o, Input in, const uint32_t *__restrict__ node_count, uint32_t *abort_flag,
+                                                        uint32_t *levels_out) {
+    __shared__ uint32_t s_depth;
+    if (threadIdx.x == 0) s_depth = 0u;
+    __syncthreads();
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t count = *node_count < o.node_capacity ? *node_count : o.node_capacity;
+    if (w != 0u && w < count) {
+        const u2 task = o.task[w];
+        if (task.x != INVALID_U32 && (task.y & TASK_FITS)) {
+            const uint32_t depth = task.y & ~TASK_FITS;
+            if (!collapse_node(t, o, in, w, task.x, depth)) atomicExch(abort_flag, 1u);
+            atomicMax(&s_depth, depth);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_depth) atomicMax(levels_out, s_depth);
+}
+
+// =====================================================================================================================
+// Small structures (n <= SMALL_BUILD_MAX): the whole build in ONE launch of one block.  test_rtx.cpp:122-139 rebuilds a
+// one-triangle mesh and a three-instance TLAS every frame; the general pipeline costs sixteen stream operations there
+// (three memsets, thirteen kernels), i.e. the launch latency sixteen times over.  Same algorithm, same functions, same
+// tree: boxes and keys in shared memory, the keys ranked against each other (n^2 / 256 comparisons per thread), the climb
+// and the collapse on the global scratch arrays with block barriers between the stages.
+// =====================================================================================================================
+constexpr uint32_t SMALL_BUILD_MAX = 512;
+constexpr int SMALL_BLOCK = 256;
+
+template<class Input>
+__global__ void __launch_bounds__(SMALL_BLOCK) k_build_small(Input in, BlobHeader *h, uint32_t flags, BlobLayout L, uint32_t *small, uint32_t *flag, u2 *task,
+                                                             uint64_t *keys, uint32_t *rec_src, f4 *pbox, Bvh2Node *node, float ci) {
+    __shared__ uint64_t skey[SMALL_BUILD_MAX];
+    __shared__ __align__(16) unsigned char node_smem[(SMALL_BLOCK / 8) * sizeof(Node8)];
+    __shared__ uint32_t s_cb[6], s_depth, s_end;
+    const uint32_t n = in.n, tid = threadIdx.x;
+    // ---- header, counters, scratch
+    for (uint32_t k = tid; k < SMALL_WORDS; k += SMALL_BLOCK) small[k] = 0u;
+    for (uint32_t k = tid; k < n; k += SMALL_BLOCK) flag[k] = 0u;
+    for (uint32_t k = tid; k < L.node_capacity; k += SMALL_BLOCK) task[k] = make_u2(INVALID_U32, 0u);
+    if (tid < 3u) s_cb[tid] = 0xffffffffu, s_cb[3 + tid] = 0u;
+    if (tid == 0u) {
+        BlobHeader hd;
+        memset(&hd, 0, sizeof(hd));
+        hd.magic = BLOB_MAGIC, hd.kind = Input::kind, hd.prim_count = n, hd.node_capacity = L.node_capacity;
+        hd.flags = flags, hd.prim_stride = L.prim_stride, hd.plant_magic = PLANT_MAGIC;
+        hd.nodes_offset = L.nodes_offset, hd.prims_offset = L.prims_offset, hd.parent_offset = L.parent_offset, hd.total_bytes = L.total_bytes;
+        for (int a = 0; a < 3; a++) hd.lo[a] = INFINITY, hd.hi[a] = -INFINITY;
+        *h = hd;
+        s_depth = 0u;
+    }
+    __syncthreads();
+    if (tid == 0u) small[SM_COUNTERS] = 1u;// the root
+    // ---- boxes and centre bounds
+    for (uint32_t i = tid; i < n; i += SMALL_BLOCK) {
+        const Box b = in.box(i);
+        pbox[2u * i] = make_f4(b.lo[0], b.lo[1], b.lo[2], 0.f), pbox[2u * i + 1u] = make_f4(b.hi[0], b.hi[1], b.hi[2], 0.f);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            const float c = 0.5f * (b.lo[a] + b.hi[a]);
+            if (c == c) atomicMin(&s_cb[a], float_to_ordered(c)), atomicMax(&s_cb[3 + a], float_to_ordered(c));
+        }
+    }
+    __syncthreads();
+    // ---- keys, ranked in shared memory (keys are unique: the primitive index sits in the low bits)
+    const uint32_t bits = morton_bits_for(n), index_bits = index_bits_for(n);
+    {
+        float clo[3], inv_ext[3];
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            clo[a] = ordered_to_float(s_cb[a]);
+            const float ext = ordered_to_float(s_cb[3 + a]) - clo[a];
+            inv_ext[a] = ext > 0.f ? 1.0f / ext : 0.f;
+            if (s_cb[a] == 0xffffffffu) clo[a] = 0.f, inv_ext[a] = 0.f;
+        }
+        for (uint32_t i = tid; i < n; i += SMALL_BLOCK)
+            skey[i] = (morton63(box_from_pbox(pbox[2u * i], pbox[2u * i + 1u]), clo, inv_ext, bits) << index_bits) | (uint64_t)i;
+    }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += SMALL_BLOCK) {
+        const uint64_t k = skey[i];
+        uint32_t rank = 0u;
+        for (uint32_t j = 0; j < n; j++) rank += skey[j] < k ? 1u : 0u;
+        keys[rank] = k;
+    }
+    __syncthreads();
+    // ---- binary hierarchy
+    Bvh2 t;
+    t.n = n, t.index_bits = index_bits, t.keys = keys, t.node = node, t.flag = flag, t.root = reinterpret_cast<Bvh2Half *>(small + SM_ROOT_HALF);
+    t.ci = ci, t.max_leaf = Input::max_leaf;
+    for (uint32_t i = tid; i < n; i += SMALL_BLOCK) {
+        const uint32_t p = t.order(i);
+        lbvh_climb(t, i, box_from_pbox(pbox[2u * p], pbox[2u * p + 1u]));
+    }
+    __threadfence_block();
+    __syncthreads();
+    // ---- wide hierarchy, level by level (the nodes of a level are the index range allocated while the previous one ran)
+    Bvh8Out o;
+    o.header = h, o.nodes = reinterpret_cast<Node8 *>(reinterpret_cast<char *>(h) + L.nodes_offset), o.prims = reinterpret_cast<char *>(h) + L.prims_offset;
+    o.parent = L.parent_offset ? reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(h) + L.parent_offset) : nullptr;
+    o.task = task, o.counters = small + SM_COUNTERS, o.node_capacity = L.node_capacity, o.rec_src = rec_src;
+    const uint32_t octets = SMALL_BLOCK / 8u, oct = tid >> 3;
+    bool failed = false;
+    for (uint32_t begin = 0u, end = 1u, depth = 1u; begin < end; depth++) {
+        for (uint32_t base = begin; base < end; base += octets) {// block-uniform trip count
+            const uint32_t w = base + oct;
+            const bool act = w < end;
+            uint32_t bid = INVALID_U32;
+            if (act && w != 0u) bid = *reinterpret_cast<volatile uint32_t *>(&task[w].x);
+            if (!collapse_octet<Input, false, false>(t, o, in, w, bid, depth, act, node_smem, small + SM_DONE, small + SM_PENDING)) failed = true;
+        }
+        __threadfence_block();
+        __syncthreads();
+        if (tid == 0u) {
+            const uint32_t count = *reinterpret_cast<volatile uint32_t *>(&small[SM_COUNTERS]);
+            s_end = count < L.node_capacity ? count : L.node_capacity;
+            s_depth = depth;
+        }
+        __syncthreads();
+        begin = end, end = s_end;
+    }
+    if (failed) small[SM_ABORT] = 1u;
+    // ---- records, header
+    uint32_t child_depth = 0u;
+    for (uint32_t j = tid; j < n; j += SMALL_BLOCK) {
+        emit_record(t, o, in, j);
+        if constexpr (Input::kind == KIND_INSTANCES) {
+            const BlobHeader *bh = InstInput::blas_of(in.inst[t.order(rec_src[j])]);
+            if (bh) child_depth = child_depth > bh->depth ? child_depth : bh->depth;
+        }
+    }
+    if constexpr (Input::kind == KIND_INSTANCES) {
+        child_depth = __reduce_max_sync(0xffffffffu, child_depth);
+        if ((tid & 31u) == 0u && child_depth) atomicMax(&small[SM_CHILD_DEPTH], child_depth);
+    }
+    __threadfence_block();
+    __syncthreads();
+    if (tid == 0u) {
+        const uint32_t levels = s_depth;
+        h->node_count = small[SM_COUNTERS], h->prim_written = small[SM_COUNTERS + COUNTER_STRIDE];
+        h->depth = levels;
+        h->max_stack = Input::kind == KIND_INSTANCES ? levels + 2u + *reinterpret_cast<volatile uint32_t *>(&small[SM_CHILD_DEPTH]) : levels;
+        bool ok = small[SM_ABORT] == 0u && *reinterpret_cast<volatile uint32_t *>(&small[SM_COUNTERS + 2 * COUNTER_STRIDE]) == n &&
+                  small[SM_COUNTERS] <= L.node_capacity;
+        uint32_t err = ok ? 0u : (small[SM_ABORT] ? small[SM_ABORT] : 3u);
+        if (ok && h->max_stack > (uint32_t)LCRT_STACK_SIZE) ok = false, err = 5u;
+        h->error = err, h->built = ok ? 1u : 0u;
+    }
 }
 
 template<class Input>
@@ -504,6 +781,24 @@ __global__ void __launch_bounds__(128) k_refit_climb(RefitCtx c, Input in) {
     if (w < c.header->node_count) refit_climb(c, in, w);
 }
 
+// small structures: the arrival counters, the records and the climb in one launch of one block
+template<class Input>
+__global__ void __launch_bounds__(SMALL_BLOCK) k_refit_small(RefitCtx c, Input in) {
+    if (!refit_allowed(c.header, in.n)) {
+        if (threadIdx.x == 0) c.header->error = 4u;
+        return;
+    }
+    const uint32_t nodes = c.header->node_count;
+    for (uint32_t w = threadIdx.x; w < nodes; w += SMALL_BLOCK) c.arrived[w] = 0u;
+    for (uint32_t j = threadIdx.x; j < in.n; j += SMALL_BLOCK) {
+        char *rec = c.prims + (uint64_t)j * Input::rec_bytes;
+        in.write(rec, Input::record_prim(rec));
+    }
+    __threadfence_block();
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w < nodes; w += SMALL_BLOCK) refit_climb(c, in, w);
+}
+
 // ---- instance buffer
 __global__ void k_instances_init(Instance *instances, uint32_t first, uint32_t count) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -518,6 +813,18 @@ __global__ void k_apply_mods(Instance *instances, const Modification *__restrict
     if (i < n) {
         Modification m;
         copy_vec16(&m, &mods[i], 5);
+        apply_modification(instances, m);
+    }
+}
+// a handful of modifications travel in the launch parameters (no staging copy): the per-frame case of test_rtx.cpp
+constexpr uint32_t INLINE_MODS_MAX = 16;
+struct InlineMods {
+    Modification m[INLINE_MODS_MAX];
+};
+__global__ void k_apply_mods_inline(Instance *instances, const __grid_constant__ InlineMods mods, uint32_t n) {
+    const uint32_t i = threadIdx.x;
+    if (i < n) {
+        Modification m = mods.m[i];
         apply_modification(instances, m);
     }
 }
@@ -613,6 +920,12 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
     const u4 *tlas_nodes = reinterpret_cast<const u4 *>(reinterpret_cast<const char *>(p.tlas) + p.tlas->nodes_offset);
     const InstanceRecord *tlas_recs = reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(p.tlas) + p.tlas->prims_offset);
     const bool single = p.tlas->prim_count == 1u;
+    if (p.tlas->max_stack > (uint32_t)LCRT_STACK_SIZE) {
+        // a hierarchy deeper than the traversal stack (never one this library built, k_build_finalize): nothing is traced,
+        // the error is raised; the caller sees it at its next synchronisation (lcbSynchronize / lcrtBlobInfo.trace_error)
+        if (threadIdx.x == 0 && blockIdx.x == 0) atomicOr(const_cast<uint32_t *>(&p.tlas->trace_error), 1u);
+        return;
+    }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t lt_mask = (1u << lane) - 1u;
     bool active = false, unsaved = false;// unsaved: this lane's finished ray has not been written yet
@@ -645,7 +958,6 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                     o[1] = make_u2(type == HIT_SURFACE ? tr.hit_rec() : 0u, 0u), o[2] = make_u2(type, as_uint(tr.hit_t()));
                 }
                 if constexpr (COUNT) c_nodes += tr.ctr.nodes, c_prims += tr.ctr.prims, c_insts += tr.ctr.insts, c_exact += tr.ctr.exact;
-                if (tr.overflowed()) atomicOr(const_cast<uint32_t *>(&p.tlas->trace_error), 1u);
                 unsaved = false;
             }
             if (exhausted) break;// every lane idle and nothing left to fetch
@@ -796,11 +1108,19 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     char *bp = static_cast<char *>(blob);
     uint32_t *small = reinterpret_cast<uint32_t *>(tp + T.small);
     BlobHeader *h = reinterpret_cast<BlobHeader *>(bp);
+    uint32_t *flag = reinterpret_cast<uint32_t *>(tp + T.flag);
+    u2 *task = reinterpret_cast<u2 *>(tp + T.task);
+    if (n != 0u && n <= SMALL_BUILD_MAX) {
+        // one launch of one block does it all (k_build_small)
+        k_build_small<Input><<<1, SMALL_BLOCK, 0, stream>>>(in, h, flags, L, small, flag, task, reinterpret_cast<uint64_t *>(tp + T.keys0),
+                                                            reinterpret_cast<uint32_t *>(tp + T.keys1), reinterpret_cast<f4 *>(tp + T.pbox),
+                                                            reinterpret_cast<Bvh2Node *>(tp + T.node), sah_ci(flags));
+        LCRT_LAUNCH_CHECK("k_build_small");
+        return LCRT_SUCCESS;
+    }
     k_build_init<<<1, 32, 0, stream>>>(h, Input::kind, n, flags, L, small);
     LCRT_LAUNCH_CHECK("k_build_init");
     if (n == 0) return LCRT_SUCCESS;
-    uint32_t *flag = reinterpret_cast<uint32_t *>(tp + T.flag);
-    u2 *task = reinterpret_cast<u2 *>(tp + T.task);
     // flag and task are adjacent in the scratch layout: arrival counters 0, tasks INVALID
     LCRT_CUDA(cudaMemsetAsync(flag, 0, (uint64_t)n * 4, stream));
     LCRT_CUDA(cudaMemsetAsync(task, 0xff, (uint64_t)L.node_capacity * 8, stream));
@@ -825,8 +1145,7 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     t.n = n, t.index_bits = index_bits, t.keys = sb.keys[cur];
     t.node = reinterpret_cast<Bvh2Node *>(tp + T.node);
     t.flag = flag, t.root = reinterpret_cast<Bvh2Half *>(small + SM_ROOT_HALF), t.ci = sah_ci(flags), t.max_leaf = Input::max_leaf;
-    // 64-thread blocks: a block lives as long as its longest climber (most threads leave after one or two levels)
-    k_climb<<<(n + 63u) / 64u, 64, 0, stream>>>(t, pbox);
+    k_climb<<<(n + CLIMB_CHUNK - 1u) / CLIMB_CHUNK, CLIMB_CHUNK, 0, stream>>>(t, pbox);
     LCRT_LAUNCH_CHECK("k_climb");
     Bvh8Out o;
     o.header = h, o.nodes = reinterpret_cast<Node8 *>(bp + L.nodes_offset), o.prims = bp + L.prims_offset;
@@ -845,10 +1164,12 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
         const uint32_t need = (L.node_capacity + COLLAPSE_BLOCK / 8u - 1u) / (COLLAPSE_BLOCK / 8u);
         if (g > need) g = need;
         // cooperative launch: the runtime guarantees that all blocks are co-resident (octets wait for their parents' tasks)
-        uint32_t *abort_flag = small + SM_ABORT, *done_flag = small + SM_DONE, *levels = small + SM_LEVELS;
+        uint32_t *abort_flag = small + SM_ABORT, *done_flag = small + SM_DONE, *levels = small + SM_LEVELS, *pending = small + SM_PENDING;
         Input in_arg = in;
-        void *args[] = {&t, &o, &in_arg, &abort_flag, &done_flag, &levels};
+        void *args[] = {&t, &o, &in_arg, &abort_flag, &done_flag, &levels, &pending};
         LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(COLLAPSE_BLOCK), args, 0, stream));
+        k_collapse_fits<Input><<<(L.node_capacity + 127u) / 128u, 128, 0, stream>>>(t, o, in, small + SM_COUNTERS, abort_flag, levels);
+        LCRT_LAUNCH_CHECK("k_collapse_fits");
     }
     k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in, small + SM_CHILD_DEPTH);
     LCRT_LAUNCH_CHECK("k_emit_records");
@@ -874,6 +1195,11 @@ static int refit_generic(cudaStream_t stream, const Input &in, void *temp, uint6
     c.parent = reinterpret_cast<const uint32_t *>(bp + L.parent_offset);
     c.box_lo = reinterpret_cast<f4 *>(tp), c.box_hi = c.box_lo + L.node_capacity;
     c.arrived = reinterpret_cast<uint32_t *>(c.box_hi + L.node_capacity);
+    if (n <= SMALL_BUILD_MAX) {
+        k_refit_small<Input><<<1, SMALL_BLOCK, 0, stream>>>(c, in);
+        LCRT_LAUNCH_CHECK("k_refit_small");
+        return LCRT_SUCCESS;
+    }
     LCRT_CUDA(cudaMemsetAsync(c.arrived, 0, (uint64_t)L.node_capacity * 4, stream));
     k_refit_records<Input><<<(n + 255u) / 256u, 256, 0, stream>>>(in, c.header, c.prims);
     LCRT_LAUNCH_CHECK("k_refit_records");
@@ -998,6 +1324,16 @@ int lcrtInstancesApplyMods(lcrtStream stream, void *instances, const void *mods_
     k_apply_mods<<<(mod_count + 255u) / 256u, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<Instance *>(instances),
                                                                                              static_cast<const Modification *>(mods_device), mod_count);
     LCRT_LAUNCH_CHECK("k_apply_mods");
+    return LCRT_SUCCESS;
+}
+
+int lcrtInstancesApplyModsHost(lcrtStream stream, void *instances, const void *mods_host, uint32_t mod_count) {
+    if (mod_count == 0) return LCRT_SUCCESS;
+    if (instances == nullptr || mods_host == nullptr || mod_count > INLINE_MODS_MAX) return LCRT_ERROR_INVALID_VALUE;
+    InlineMods p;
+    memcpy(p.m, mods_host, (size_t)mod_count * sizeof(Modification));
+    k_apply_mods_inline<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<Instance *>(instances), p, mod_count);
+    LCRT_LAUNCH_CHECK("k_apply_mods_inline");
     return LCRT_SUCCESS;
 }
 

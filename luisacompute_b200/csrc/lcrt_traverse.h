@@ -460,6 +460,7 @@ struct Traversal {
         // it can not see through goes into a register once and the selectors become immediates (as in the batch kernel,
         // where it is a kernel parameter).
         magic = tlas->plant_magic;
+        check_stack_bound(tlas->max_stack);
     }
 
     // ---- result (valid once step() has returned false).  hit_rec / hit_pi locate a surface hit for refine_surface_hit.
@@ -530,15 +531,17 @@ struct Traversal {
         octinv = RAY_PENDING;
     }
 
-    // Guarded push.  The builder bounds the stack need (TLAS levels + 2 + deepest BLAS levels, recorded in
-    // BlobHeader::depth / max_stack and checked by k_build_finalize), so the guard never fires on a structure this
-    // library built; on a foreign or corrupted blob it ends the ray and raises STACK_OVERFLOW (reported through
-    // BlobHeader::trace_error by the callers) instead of overrunning the per-ray storage.
+    // The stack can not overflow on a structure this library built: the builder records the depth of every hierarchy
+    // (BlobHeader::depth), a TLAS build adds up the most entries a ray can need (max_stack = TLAS depth + 2 + deepest
+    // instanced BLAS) and refuses to mark itself built beyond LCRT_STACK_SIZE (k_build_finalize, error 5).  The traversal
+    // checks that bound ONCE per ray, in init(), instead of guarding every push (a compare and a branch per node cost the
+    // batch kernel 5 % — profiles/r2_trace_guard.md): a blob that claims more ends the ray at once and raises
+    // STACK_OVERFLOW, which the callers report through BlobHeader::trace_error.
     static constexpr uint32_t STACK_OVERFLOW = 0x80000000u;// flag bit in ray_mask (the mask itself is 8 bits)
     LCRT_HD bool overflowed() const { return (ray_mask & STACK_OVERFLOW) != 0u; }
-    LCRT_HD void push(u2 v) {
-        if (sp < LCRT_STACK_SIZE) store->store(sp++, v);
-        else ray_mask |= STACK_OVERFLOW, done = true;
+    LCRT_HD void push(u2 v) { store->store(sp++, v); }
+    LCRT_HD void check_stack_bound(uint32_t max_stack) {
+        if (max_stack > (uint32_t)LCRT_STACK_SIZE) ray_mask |= STACK_OVERFLOW, done = true;
     }
 
     LCRT_HD void enter_instance(uint32_t rec_index, const u4 r3, const u4 r4) {

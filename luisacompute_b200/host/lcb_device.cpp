@@ -301,8 +301,11 @@ struct Accel final : Resource {
         primitives.resize(instance_count, nullptr);
         prim_handles.resize(instance_count, 0ull);
         // ---- upload the modifications and apply them (cuda_accel.cpp:176-240)
+        Modification few[16];// a handful of modifications go out in the launch parameters (lcrtInstancesApplyModsHost)
+        const bool inline_mods = n != 0u && n <= 16u;
         if (n) {
-            LCB_CHECK(stage_mods(stream, n));
+            if (!inline_mods) LCB_CHECK(stage_mods(stream, n));
+            Modification *h_mods = inline_mods ? few : this->h_mods;
             memcpy(h_mods, in_mods, (size_t)n * sizeof(Modification));
             uint64_t last_handle = ~0ull;
             Primitive *last_prim = nullptr;
@@ -328,9 +331,13 @@ struct Accel final : Resource {
                 prim_handles[m.index] = last_prim->native();
                 if (last_prim->tag == Resource::Tag::PROCEDURAL) m.flags |= lcrt::MOD_PROCEDURAL;
             }
-            LCB_CUDA(cudaMemcpyAsync(d_mods, h_mods, (size_t)n * sizeof(Modification), cudaMemcpyHostToDevice, stream));
-            LCB_CUDA(cudaEventRecord(staged, stream));
-            LCB_CHECK(lcrtInstancesApplyMods(stream, instance_buffer, d_mods, n));
+            if (inline_mods) {
+                LCB_CHECK(lcrtInstancesApplyModsHost(stream, instance_buffer, h_mods, n));
+            } else {
+                LCB_CUDA(cudaMemcpyAsync(d_mods, h_mods, (size_t)n * sizeof(Modification), cudaMemcpyHostToDevice, stream));
+                LCB_CUDA(cudaEventRecord(staged, stream));
+                LCB_CHECK(lcrtInstancesApplyMods(stream, instance_buffer, d_mods, n));
+            }
         }
         // ---- BLAS handles that changed through a rebuild without a modification (cuda_accel.cpp:244-258, 286-308): the
         // reference scans every instance on every build; here the scan only runs when some primitive's blob has moved

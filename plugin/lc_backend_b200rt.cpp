@@ -75,8 +75,11 @@ public:
         info.native_handle = reinterpret_cast<void *>(address);
         return info;
     }
-    [[nodiscard]] BufferCreationInfo create_buffer(const ir::CArc<ir::Type> *, size_t, void *) noexcept override {
-        LCB_UNSUPPORTED("create_buffer from an IR type");
+    // the flat C API (src/api/runtime.cpp:341-353) creates every buffer through this overload; without the Rust IR library an
+    // element type can not be named, so a null type means "bytes" (what a C caller passes), anything else is unsupported
+    [[nodiscard]] BufferCreationInfo create_buffer(const ir::CArc<ir::Type> *element, size_t elem_count, void *external_memory) noexcept override {
+        if (element != nullptr) { LCB_UNSUPPORTED("create_buffer from an IR type"); }
+        return create_buffer(static_cast<const Type *>(nullptr), elem_count, external_memory);
     }
     void destroy_buffer(uint64_t handle) noexcept override { lcbBufferDestroy(_device, handle); }
 
@@ -210,6 +213,13 @@ public:
     void visit(MotionInstanceBuildCommand *) noexcept override { LCB_UNSUPPORTED("MotionInstanceBuildCommand"); }
     void visit(BindlessArrayUpdateCommand *) noexcept override { LCB_UNSUPPORTED("BindlessArrayUpdateCommand"); }
 
+    [[nodiscard]] int trace_flat(uint64_t stream, uint32_t mode, uint64_t accel, uint64_t rays, uint64_t hits, uint64_t count, uint32_t mask) noexcept {
+        auto s = reinterpret_cast<lcrtStream>(stream);
+        if (mode == 0u) { return lcbTraceClosest(_device, s, accel, reinterpret_cast<const void *>(rays), count, nullptr, mask, reinterpret_cast<void *>(hits), nullptr); }
+        if (mode == 1u) { return lcbTraceAny(_device, s, accel, reinterpret_cast<const void *>(rays), count, nullptr, mask, reinterpret_cast<uint32_t *>(hits), nullptr); }
+        return LCRT_ERROR_INVALID_VALUE;
+    }
+
     // ---- everything outside the ray-tracing path
     [[nodiscard]] ResourceCreationInfo create_texture(PixelFormat, uint, uint, uint, uint, uint, bool, bool) noexcept override { LCB_UNSUPPORTED("create_texture"); }
     void destroy_texture(uint64_t) noexcept override {}
@@ -238,6 +248,16 @@ LUISA_EXPORT_API luisa::compute::DeviceInterface *create(luisa::compute::Context
 
 LUISA_EXPORT_API void destroy(luisa::compute::DeviceInterface *device) noexcept {
     luisa::delete_with_allocator(static_cast<luisa::compute::b200rt::Device *>(device));
+}
+
+// Flat C entry for callers that can not build a CustomCommand (the reference's C API, src/api/runtime.cpp:487-568, has no
+// custom-command variant): traces `count` rays of `ray_buffer` against `accel` on `stream`, stream-ordered like a
+// ShaderDispatchCommand.  mode: 0 closest -> SurfaceHit[count], 1 any -> uint[count].  `device` is the DeviceInterface pointer the C
+// API hands around as LCDevice._0; handles are the C API's.
+LUISA_EXPORT_API int b200rt_trace(void *device, uint64_t stream, uint32_t mode, uint64_t accel, uint64_t ray_buffer, uint64_t hit_buffer,
+                                  uint64_t count, uint32_t visibility_mask) noexcept {
+    auto d = static_cast<luisa::compute::b200rt::Device *>(static_cast<luisa::compute::DeviceInterface *>(device));
+    return d->trace_flat(stream, mode, accel, ray_buffer, hit_buffer, count, visibility_mask);
 }
 
 LUISA_EXPORT_API void backend_device_names(luisa::vector<luisa::string> &names) noexcept {

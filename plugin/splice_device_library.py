@@ -11,9 +11,9 @@ lcrt_device_library.cuh over the BVH8 format) instead of OptiX hit-object traver
     `params.ls_kid`, lc_synchronize_block) — the generated `extern "C" __global__ void __raygen__main()` reading
     `__constant__ Params params` is then launched with cuLaunchKernel by plugin/hybrid/b200_shader_rt.cpp, no OptiX
     module / pipeline / SBT / optixLaunch (cuda_shader_optix.cpp:49-309, 478-483).  The code generator emits no
-    out-of-range guard for RT kernels (cuda_codegen_ast.cpp:1470-1472: OptiX launches exactly dispatch_size threads), so
-    `lc_dispatch_id()` — used exactly once, in `const auto did = lc_dispatch_id();` (:1504) right after `ls` — becomes a macro
-    that also returns from threads outside the dispatch, the same test the native branch's kernels carry.
+    out-of-range guard for RT kernels (cuda_codegen_ast.cpp:1470-1472: OptiX launches exactly dispatch_size threads), so the
+    entry point's NAME becomes a function-like macro that wraps the generated body into an entry point with that guard, the
+    same test the native branch's kernels carry.
 Nothing of the reference is stored in this repository: the input is read from the reference tree (or from a kernel source the
 reference dumped with LUISA_DUMP_SOURCE=1) at build / test time.
 usage: python plugin/splice_device_library.py IN OUT [--library FILE]   (IN: cuda_device_resource.h or a dumped kernel_*.cu)
@@ -57,14 +57,25 @@ def splice(text: str, library: str, native_launch: bool = True) -> str:
     # the native branch's helpers, taken from the reference text at build time: "#else" ... up to its "#endif"
     nat0 = n + len("#else\n")
     nat1 = text.index("\n#endif", text.index("lc_synchronize_block", nat0))
-    native = text[nat0:nat1].replace("inline auto lc_dispatch_id() noexcept", "inline auto lc_native_dispatch_id() noexcept")
-    assert "lc_native_dispatch_id" in native and "threadIdx" in native and "_optix_" not in native
+    native = text[nat0:nat1]
+    assert "lc_dispatch_id" in native and "threadIdx" in native and "_optix_" not in native
     optix_branch = (
         "#ifdef LUISA_ENABLE_OPTIX\n\n"
         "// ray-tracing kernels are launched natively (cuLaunchKernel): launch-index helpers of the reference's native branch\n"
         + native + "\n\n"
-        "// the code generator emits no out-of-range guard for ray-tracing kernels: `const auto did = lc_dispatch_id();` gets it here\n"
-        "#define lc_dispatch_id() lc_native_dispatch_id(); if (lc_any(did >= ls)) { return; } static_cast<void>(0)\n\n")
+        "// The code generator emits no out-of-range guard for ray-tracing kernels (OptiX launches exactly dispatch_size threads) and\n"
+        "// writes the entry point as `extern \"C\" __global__ void __raygen__main() { body }` (cuda_codegen_ast.cpp:1391-1394).  As a\n"
+        "// function-like macro the name turns that text into: the declaration of an unused kernel, the real entry point (still called\n"
+        "// __raygen__main: a macro is not re-expanded inside its own expansion) that drops the threads outside the dispatch, and the\n"
+        "// generated body as an inlined function.  Handlers outlined by the RayQuery lowering re-read the built-in variables and the\n"
+        "// kernel arguments through the module-wide `__constant__ Params params` (:446-521), which is why the arguments stay there.\n"
+        "#define __raygen__main() lc_rt_unused_entry(); \\\n"
+        "    static __device__ __forceinline__ void lc_rt_kernel_body(); \\\n"
+        "    extern \"C\" __global__ void __raygen__main() { \\\n"
+        "        if (lc_any(lc_dispatch_id() >= lc_dispatch_size())) { return; } \\\n"
+        "        lc_rt_kernel_body(); \\\n"
+        "    } \\\n"
+        "    static __device__ __forceinline__ void lc_rt_kernel_body()\n\n")
     if not native_launch:
         # developer variant (plugin/hybrid/build.sh HYBRID_OPTIX_LAUNCH=1 -> lc-backend-b200o): the kernel stays an OptiX raygen
         # program launched by the reference's CUDAShaderOptiX, only the traversal is ours — used to tell launch-path effects

@@ -12,6 +12,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A GPU test that hangs (a kernel that never ends) must end the run, not sit on the GPU box until somebody kills it:
+    with pytest-timeout present every GPU test gets 15 minutes, enforced from a watchdog thread (it can end the process
+    while the main thread is stuck inside a CUDA call)."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 @pytest.fixture(scope="session")
 def oracle():
     from oracle import oracle_py

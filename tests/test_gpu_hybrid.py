@@ -53,9 +53,11 @@ def test_reference_test_programs_render_the_same_image(tmp_path):
     # test_procedural's sphere handler is numerically fragile by construction (d = sqrt(d_oc^2 - tc^2) goes NaN within rounding of a
     # sphere's centre, `d <= radius` flips within rounding of its silhouette): whether a mul and a sub of the USER'S handler are fused
     # into an FMA decides those pixels, and the driver's PTX compiler (native launch, `b200`) does not fuse exactly like OptiX's.  With
-    # the kernels launched through OptiX (`b200o`, same traversal, same BVH) the images equal the reference's; natively 772 of 921 600
-    # pixels differ (436 within 2 px of a projected sphere centre, the rest on silhouettes; profiles/r2_native_launch.md).
-    for test, tol_pixels, tol_optix in (("test_rtx", 64, 64), ("test_procedural", 1600, 0), ("test_procedural_callable", 1600, 0), ("test_indirect_rtx", 64, 64)):
+    # the kernels launched through OptiX (`b200o`, same traversal, same BVH) the images equal the reference's to 0-30 pixels (0 with the
+    # traversal out of line as in round 1, 30 with it inlined into the single RayQuery site: inlining changes what the compiler fuses
+    # in the handler too); natively 772 of 921 600 pixels differ (436 within 2 px of a projected sphere centre, the rest on
+    # silhouettes; profiles/r2_native_launch.md).
+    for test, tol_pixels, tol_optix in (("test_rtx", 64, 64), ("test_procedural", 1600, 100), ("test_procedural_callable", 1600, 100), ("test_indirect_rtx", 64, 64)):
         e = res[test]
         if "unavailable" in e:
             continue
@@ -93,3 +95,32 @@ def test_b200_backend_runs_without_optix(tmp_path):
                 loaded += open(str(d / f), errors="replace").read()
         assert "liblc-backend-b200" in loaded and "liblcb200_rt" in loaded      # the log does see what is loaded...
         assert "nvoptix" not in loaded and "nvrtcore" not in loaded             # ...and OptiX is not
+
+
+def test_d6_shadow_rays_ending_on_the_light(tmp_path):
+    """Divergence D6: a ray whose t_max is exactly the distance of a surface.  This repository accepts t <= t_max
+    like the oracle and Embree do (hit iff tnear <= t <= tfar; accel.rs:449-535 hands the interval to rtcIntersect1 / rtcOccluded1
+    unchanged), decided exactly; OptiX decides the same comparison in fp32 and mostly misses.  It shows in test_path_tracing-style
+    next-event estimation, where the shadow ray ends ON the light quad: C5 renders 2-3 % darker here than on the reference's CUDA
+    backend.  north_star names the Embree backend as the parity reference, so the inclusive rule stays; this test bounds the
+    visible difference and pins its mechanism: with the shadow rays shortened by 0.1 % both backends render the same image."""
+    exe = os.path.join(BIN, "c5_dsl_path_tracer")
+    if not (os.path.exists(exe) and os.path.exists(os.path.join(BIN, "liblc-backend-cuda.so"))):
+        pytest.skip("C5 DSL program / reference CUDA backend not built")
+    res = {}
+    for name, scale in (("as_written", None), ("shortened", "0.999")):
+        out = str(tmp_path / f"c5_{name}.json")
+        env = _env(**({"C5_SHADOW_TMAX_SCALE": scale} if scale else {}))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ref_optix_c5.py"), "--width", "640", "--height", "360", "--spp", "16",
+                            "--dir", str(tmp_path / name), "--out", out], capture_output=True, text=True, timeout=900, env=env)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res[name] = json.load(open(out))
+        if "unavailable" in res[name].get("cuda", {}):
+            pytest.skip("the reference's cuda backend did not start on this box: " + res[name]["cuda"]["unavailable"][-200:])
+        assert "unavailable" not in res[name]["b200"], res[name]["b200"]
+    a, s = res["as_written"]["image_agreement"], res["shortened"]["image_agreement"]
+    rel = (a["mean_radiance_cuda"] - a["mean_radiance_b200"]) / a["mean_radiance_cuda"]
+    print(f"D6: mean radiance cuda {a['mean_radiance_cuda']:.5f} b200 {a['mean_radiance_b200']:.5f} ({100 * rel:.2f} % darker); "
+          f"with shadow rays x 0.999: {s['mean_radiance_cuda']:.5f} vs {s['mean_radiance_b200']:.5f}")
+    assert 0.0 <= rel < 0.05, a                                    # darker, by a few per cent, never brighter
+    assert abs(s["mean_radiance_cuda"] - s["mean_radiance_b200"]) < 2e-3 * s["mean_radiance_cuda"], s

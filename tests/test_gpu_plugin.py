@@ -159,3 +159,36 @@ def test_plugin_plumbing_entry_points():
     L.lcbStreamDestroy(h, s0), L.lcbStreamDestroy(h, s1)
     L.lcbBufferDestroy(h, a), L.lcbBufferDestroy(h, b)
     dev.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(BIN, "test_c_api_rtx")), reason="flat C API program not built (need the reference tree; make -C plugin)")
+def test_flat_c_api_drives_the_plugin(oracle, tmp_path):
+    """a plain-C program over the reference's flat C API (include/luisa/api/api.h; liblc-api.so is the reference's
+    src/api/runtime.cpp + logging.cpp compiled where they lie) creates the mesh / accel, builds them through an LCCommandList
+    (LCMeshBuildCommand, LCAccelBuildCommand with LCAccelBuildModification records) on the `b200rt` plugin and traces the
+    test_rtx.cpp scene; its hit records must meet the oracle's on the same scene and rays."""
+    out = str(tmp_path / "c_api_hits.bin")
+    w = h = 320
+    env = dict(os.environ, LD_LIBRARY_PATH=BIN + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([os.path.join(BIN, "test_c_api_rtx"), out, str(w), str(h)], capture_output=True, text=True, timeout=300, env=env, cwd=str(tmp_path))
+    assert r.returncode == 0, (r.returncode, (r.stdout + r.stderr)[-1500:])
+    raw = open(out, "rb").read()
+    assert struct.unpack_from("<II", raw, 0) == (w, h)
+    n = w * h
+    xf = np.frombuffer(raw, dtype="<f4", count=24, offset=8).reshape(2, 12).copy()
+    rays = np.frombuffer(raw, dtype=S.RAY_DTYPE, count=n, offset=8 + 96).copy()
+    got = np.frombuffer(raw, dtype=S.HIT_DTYPE, count=n, offset=8 + 96 + 32 * n).copy()
+    occ = np.frombuffer(raw, dtype="<u4", count=n, offset=8 + 96 + 56 * n).copy()
+    verts, tris, xf_ref = S.test_rtx_scene()
+    np.testing.assert_allclose(xf, np.asarray(xf_ref), atol=1e-6)               # the program does build test_rtx.cpp's instances
+    np.testing.assert_allclose(rays["o"], S.test_rtx_rays(w, h)["o"], atol=1e-6)
+    om = oracle.OracleMesh(verts, tris)
+    oa = oracle.OracleAccel()
+    oa._keep = [om]
+    assert oa.update(2, S.make_mods([om.handle, om.handle], [xf[0], xf[1]])) == 0
+    res = oracle.compare_closest(oa, rays, got)
+    assert res["id_mismatch"] == 0 and res["t_bad"] == 0 and res["bary_bad"] == 0, res
+    assert res["exact"] + res["tie"] + res["grazing"] == n and res["tie"] + res["grazing"] <= 8, res
+    assert np.array_equal(occ != 0, got["inst"] != 0xFFFFFFFF)
+    assert 10_000 < np.count_nonzero(got["inst"] != 0xFFFFFFFF) < n

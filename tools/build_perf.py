@@ -31,7 +31,7 @@ v, t = S.icosphere(8)
 m = dev.create_mesh(v, t).build()
 ms = timeit(lambda: m.build(lc.FORCE_BUILD))
 i = m.info()
-out.append(f"ico8 {len(t)} tris: {ms:.3f} ms = {len(t) / ms / 1e3:.0f} Mtris/s nodes {i.node_count} err {i.error}")
+out.append(f"ico8 {len(t)} tris: {ms:.3f} ms = {len(t) / ms / 1e3:.0f} Mtris/s nodes {i.node_count} depth {i.depth} err {i.error}")
 n = 5_000_000
 g = torch.Generator(device="cuda").manual_seed(1)
 c = torch.rand((n, 3), device="cuda", generator=g)
@@ -43,6 +43,6 @@ tris = torch.arange(3 * n, dtype=torch.int32, device="cuda").view(-1, 3)
 m2 = dev.create_mesh(verts.view(-1, 4), tris, vertex_stride=16).build()
 ms = timeit(lambda: m2.build(lc.FORCE_BUILD), reps=3, warm=1)
 i = m2.info()
-out.append(f"soup {n} tris: {ms:.3f} ms = {n / ms / 1e3:.0f} Mtris/s nodes {i.node_count} err {i.error}")
+out.append(f"soup {n} tris: {ms:.3f} ms = {n / ms / 1e3:.0f} Mtris/s nodes {i.node_count} depth {i.depth} err {i.error}")
 print(os.environ.get("LCB200_RT_LIB", "default").split("/")[-1], "|", " | ".join(out), flush=True)
 dev.close()
