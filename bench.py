@@ -15,8 +15,9 @@ Workload (BASELINE.json configs[1], "C2"): displaced icosphere level 8 (1 310 72
 Multi-GPU (torchrun, one rank per GPU): replicated scene — rank 0 builds the BLAS, NCCL-broadcasts the position-
 independent blob, every rank builds its own TLAS — and rays are sharded by 65 536-ray tiles round-robin.  The headline stays
 the C2 step with the per-GPU work fixed ("weak": every rank traces 8 388 608 rays per step), and for N > 1 the timed region
-INCLUDES gathering every rank's 24-byte hit records into ray order on rank 0 (NCCL send/recv over NVLink, chunk by chunk on
-a side stream while the next chunk is traced: luisacompute_b200.dist.HitGatherer).  `detail.c4_strong` is BASELINE config 4
+INCLUDES getting every rank's 24-byte hit records into ray order on rank 0: the trace's refine pass stores them straight into
+rank 0's framebuffer, mapped into every rank over NVLink (luisacompute_b200.dist.PeerFramebuffer, lcrtTraceClosestTiled); where
+CUDA IPC is unavailable, or with LCB_GATHER=nccl, NCCL send/recv chunk by chunk on a side stream (dist.HitGatherer).  `detail.c4_strong` is BASELINE config 4
 at every N (1 included): 50 M-triangle soup built on rank 0 and broadcast, the FIXED batch of 64 Mi rays tile-sharded over
 the ranks (strong scaling) with the same in-region gather.
 """
@@ -203,6 +204,39 @@ def reference_gpu(verts, tris, primary, bounce, backend: str = "cuda") -> dict:
 CHUNK_TILES = 8     # tiles per trace launch / gather in the multi-GPU step (512 Ki rays, 12.6 MB of hit records)
 
 
+def make_peer_framebuffer(dev, n_local_tiles: int):
+    """The gathering rank's framebuffer mapped into every rank (luisacompute_b200.dist.PeerFramebuffer), or None where CUDA IPC /
+    peer access is not available (or LCB_GATHER=nccl): the callers then gather with NCCL send / recv (HitGatherer).  Collective."""
+    import torch
+    import torch.distributed as dist
+    from luisacompute_b200.dist import PeerFramebuffer
+    ok, fb = 1, None
+    if os.environ.get("LCB_GATHER", "peer") != "peer":
+        ok = 0
+    else:
+        try:
+            fb = PeerFramebuffer(dev, n_local_tiles)
+        except Exception as e:   # noqa: BLE001 - reported, and every rank falls back together
+            print(f"[bench] rank {dist.get_rank()}: peer framebuffer unavailable ({e}); NCCL gather instead", file=sys.stderr)
+            ok = 0
+    t = torch.tensor([ok], dtype=torch.int32, device=dev.torch_device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    if int(t.item()) == 0:
+        if fb is not None:
+            fb.address = 0   # not collective any more: leave the mapping to process exit
+        return None
+    return fb
+
+
+def gather_description(fb, gat) -> str:
+    if fb is not None:
+        return ("peer framebuffer: every rank's refine pass stores its 24-byte records straight into rank 0's ray-ordered buffer over NVLink "
+                "(CUDA IPC mapping, lcrtTraceClosestTiled); one completion all-reduce per step, no gather collective, no reorder copy")
+    if gat is not None:
+        return "NCCL send / recv of 24-byte records, chunk by chunk on a side stream, one strided reorder copy per chunk (HitGatherer)"
+    return "single GPU"
+
+
 def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
     """BASELINE config 4, strong scaling: 50 M random triangles (built on rank 0, blob broadcast over NCCL), the fixed batch of
     64 Mi uniform rays in 65 536-ray tiles dealt round-robin, hit records gathered into ray order on rank 0 inside the timed
@@ -275,20 +309,31 @@ def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
     del rays
     n_local = n_tiles_local * TILE
     hits = torch.empty((n_local, 6), dtype=torch.int32, device=tdev)
-    gat = HitGatherer(n_tiles_local, tdev, chunk_tiles=2 * CHUNK_TILES) if world > 1 else None
+    gat, fb = None, None
+    if world > 1:
+        fb = make_peer_framebuffer(dev, n_tiles_local)
+        if fb is None:
+            gat = HitGatherer(n_tiles_local, tdev, chunk_tiles=2 * CHUNK_TILES)
+    out["gather"] = gather_description(fb, gat)
     lb = local.view(torch.uint8)
     ct = 2 * CHUNK_TILES
 
     def step():
+        if fb is not None:
+            # one launch; the refine pass stores every record into rank 0's ray-ordered framebuffer over NVLink
+            fb.trace_closest(acc, lb, scratch=hits)
+            fb.complete()
+            return
+        if gat is None:
+            acc.trace_closest(lb, out=hits)     # one GPU: one launch, records in place
+            return
         for t0 in range(0, n_tiles_local, ct):
             t1 = min(t0 + ct, n_tiles_local)
             acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
-            if gat is not None:
-                ev = torch.cuda.Event()
-                ev.record()
-                gat.submit(hits[t0 * TILE:t1 * TILE], t0, t1, ev)
-        if gat is not None:
-            gat.finish()
+            ev = torch.cuda.Event()
+            ev.record()
+            gat.submit(hits[t0 * TILE:t1 * TILE], t0, t1, ev)
+        gat.finish()
     step()
     barrier()
     reps = 3
@@ -299,12 +344,15 @@ def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1) / reps
-    # the trace alone (no gather), same chunking
+    # the trace alone (records stay on this rank)
     t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0e.record()
-    for t0 in range(0, n_tiles_local, ct):
-        t1 = min(t0 + ct, n_tiles_local)
-        acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
+    if gat is None:
+        acc.trace_closest(lb, out=hits)
+    else:
+        for t0 in range(0, n_tiles_local, ct):
+            t1 = min(t0 + ct, n_tiles_local)
+            acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
     t1e.record()
     torch.cuda.synchronize()
     trace_ms = t0e.elapsed_time(t1e)
@@ -317,13 +365,15 @@ def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
         allc = [torch.zeros_like(chk) for _ in range(world)] if rank == 0 else None
         dist.gather(chk, allc, 0)
         if rank == 0:
-            fb = gat.full.view(n_tiles_local, world, TILE, 6)
+            fbv = (fb if fb is not None else gat).full.view(n_tiles_local, world, TILE, 6)
             for rr in range(world):
-                assert int(fb[:, rr, :, 0].long().sum()) == int(allc[rr][0]) and int(fb[:, rr, :, 1].long().sum()) == int(allc[rr][1]), f"gather mismatch, rank {rr}"
-            assert torch.equal(fb[:, 0].reshape(-1, 6), hits)
+                assert int(fbv[:, rr, :, 0].long().sum()) == int(allc[rr][0]) and int(fbv[:, rr, :, 1].long().sum()) == int(allc[rr][1]), f"gather mismatch, rank {rr}"
+            assert torch.equal(fbv[:, 0].reshape(-1, 6), hits)
     out.update(ms_per_step=ms, mrays_s=n_rays / ms / 1e3, trace_only_ms=trace_ms, trace_only_mrays_s=n_rays / trace_ms / 1e3,
                gather_bytes_per_step=(world - 1) * n_local * 24 if world > 1 else 0, hit_fraction=float((hits[:, 0] != -1).float().mean().item()))
-    del gat, hits, local, lb, acc, mesh
+    if fb is not None:
+        fb.close()
+    del gat, fb, hits, local, lb, acc, mesh
     torch.cuda.empty_cache()
     return out
 
@@ -478,16 +528,25 @@ def main():
     # N = 1: one launch per batch.  N > 1: the same rays in chunks of CHUNK_TILES tiles, each chunk's hit records gathered
     # into ray order on rank 0 (side stream) while the next chunk is traced; the step ends when the gather has.
     K, W = args.steps, max(args.warmup, 3)
-    gat_p = gat_b = None
+    gat_p = gat_b = fb_p = fb_b = None
     n_tiles = n // TILE
     if world > 1:
         from luisacompute_b200.dist import HitGatherer
         assert n % TILE == 0
+        fb_p = make_peer_framebuffer(dev, n_tiles)
+        fb_b = make_peer_framebuffer(dev, n_tiles) if fb_p is not None else None
+        if fb_b is None:
+            fb_p = None
         gat_p, gat_b = HitGatherer(n_tiles, tdev, chunk_tiles=CHUNK_TILES), HitGatherer(n_tiles, tdev, chunk_tiles=CHUNK_TILES)
+    # scratch for the traversal's provisional records when the final ones go to the peer framebuffer
+    d_scr = torch.empty((n, 6), dtype=torch.int32, device=tdev) if fb_p is not None else None
 
     def trace_batch(d_rays, d_hits, gat):
         if gat is None:
             acc.trace_closest(d_rays, out=d_hits)
+            return
+        if fb_p is not None:
+            (fb_p if gat is gat_p else fb_b).trace_closest(acc, d_rays, scratch=d_scr)
             return
         for t0 in range(0, n_tiles, CHUNK_TILES):
             t1 = min(t0 + CHUNK_TILES, n_tiles)
@@ -497,7 +556,9 @@ def main():
             gat.submit(d_hits[t0 * TILE:t1 * TILE], t0, t1, e)
 
     def end_step():
-        if gat_p is not None:
+        if fb_p is not None:
+            fb_b.complete()     # one all-reduce orders rank 0's stream behind every rank's launches of the step
+        elif gat_p is not None:
             gat_p.finish(), gat_b.finish()
 
     for _ in range(W):
@@ -528,6 +589,9 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, tp_ms, tb_ms = (float(x) for x in t.cpu())
         # the gather by itself (nothing to hide behind): one batch, all chunks
+        for t0 in range(0, n_tiles, CHUNK_TILES):   # (warm-up: NCCL sets its send / recv channels up on first use)
+            gat_b.submit(d_hits_b[t0 * TILE:min(t0 + CHUNK_TILES, n_tiles) * TILE], t0, min(t0 + CHUNK_TILES, n_tiles), None)
+        gat_b.finish()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
@@ -545,12 +609,12 @@ def main():
         allc = [torch.zeros_like(chk) for _ in range(world)] if rank == 0 else None
         dist.gather(chk, allc, 0)
         if rank == 0:
-            for gat, base in ((gat_p, 0), (gat_b, 2)):
+            for gat, base in ((fb_p if fb_p is not None else gat_p, 0), (fb_b if fb_b is not None else gat_b, 2)):
                 fb = gat.full.view(n_tiles, world, TILE, 6)
                 for rr in range(world):
                     assert int(fb[:, rr, :, 0].long().sum()) == int(allc[rr][base]) and int(fb[:, rr, :, 1].long().sum()) == int(allc[rr][base + 1]), \
                         f"gathered hit records of rank {rr} differ from what it traced"
-            assert torch.equal(gat_p.full.view(n_tiles, world, TILE, 6)[:, 0].reshape(-1, 6), d_hits_p)
+            assert torch.equal((fb_p if fb_p is not None else gat_p).full.view(n_tiles, world, TILE, 6)[:, 0].reshape(-1, 6), d_hits_p)
     ms_per_step = total_ms / K
     value = world * 2 * n / (ms_per_step * 1e-3) / 1e6
 
@@ -624,8 +688,11 @@ def main():
 
     # ------------------------------------------------------------------ BASELINE config 4, strong scaling (detail)
     c4 = None
+    gather_text = gather_description(fb_p, gat_p)
     if not args.no_c4:
-        del gat_p, gat_b
+        if fb_p is not None:
+            fb_p.close(), fb_b.close()
+        fb_p = fb_b = gat_p = gat_b = d_scr = None
         torch.cuda.empty_cache()
         try:
             c4 = c4_strong(args, lc, dev, world, rank, barrier)
@@ -694,14 +761,18 @@ def main():
                        "incoherent_any_mrays_s": n / (any_ms * 1e-3) / 1e6, "primary_hit_fraction": hit_frac_p,
                        "blas_build_ms": build_ms, "blas_build_mtris_s": (ntris / (build_ms * 1e-3) / 1e6) if build_ms else None,
                        "numa_binding": list(numa) if numa else None, "bvh_nodes": info.node_count, "bvh_bytes": info.total_bytes, "bvh_broadcast_ms": bcast_ms, "hit_gather_ms": gather_ms,
-                       "hit_gather_note": None if world == 1 else f"one batch ({(world - 1) * n * 24 / 1e6:.0f} MB into rank 0) gathered alone, nothing to overlap with; in the step it hides behind the traces",
+                       "hit_gather": gather_text,
+                       "hit_gather_note": None if world == 1 else (f"hit_gather_ms = NCCL send/recv gather of one batch ({(world - 1) * n * 24 / 1e6:.0f} MB into rank 0) by itself, for comparison"
+                                                                   + ("; the timed step does not use it" if gather_text.startswith("peer") else "; in the step it hides behind the traces")),
                        "c4_strong": c4,
                        "scene_gen_s": gen_s},
             "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin_backend": dropin, "e2e": e2e, "clocks": clocks,
             # per step: k_trace + k_refine_hits per launch; one launch per batch at N = 1, one per CHUNK_TILES tiles otherwise
-            "gpu_launches": 4 * K if world == 1 else 4 * K * ((n_tiles + CHUNK_TILES - 1) // CHUNK_TILES),
+            "gpu_launches": 4 * K if (world == 1 or gather_text.startswith("peer")) else 4 * K * ((n_tiles + CHUNK_TILES - 1) // CHUNK_TILES),
         }
         print(json.dumps(line))
+    if fb_p is not None:
+        fb_p.close(), fb_b.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -98,6 +98,18 @@ LCRT_API int lcbTraceClosest(lcbDevice *device, lcrtStream stream, uint64_t acce
                              const uint32_t *masks, uint32_t mask, void *hits, uint64_t *counters);
 LCRT_API int lcbTraceAny(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count,
                          const uint32_t *masks, uint32_t mask, uint32_t *occluded, uint64_t *counters);
+/* lcbTraceClosest with the records written into a tiled framebuffer, possibly in a peer GPU's memory (lcrtTraceClosestTiled) */
+LCRT_API int lcbTraceClosestTiled(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count,
+                                  const uint32_t *masks, uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays,
+                                  uint64_t tile_stride_bytes, uint64_t *counters);
+/* A framebuffer other processes of this node can write into (one process per GPU): Create allocates `bytes` on
+ * this device and fills the 64-byte handle the owner hands to its peers (any channel: a torch.distributed broadcast, a
+ * file); Open maps it into the calling process (peer access over NVLink / PCIe is enabled on first use) and returns the
+ * address kernels of this device can store to; Close unmaps; Destroy frees (owner only). */
+LCRT_API int lcbFramebufferCreate(lcbDevice *device, uint64_t bytes, uint64_t *address, unsigned char handle[64]);
+LCRT_API int lcbFramebufferOpen(lcbDevice *device, const unsigned char handle[64], uint64_t *address);
+LCRT_API int lcbFramebufferClose(lcbDevice *device, uint64_t address);
+LCRT_API int lcbFramebufferDestroy(lcbDevice *device, uint64_t address);
 LCRT_API int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
                       uint32_t mask, int terminate_on_first, uint32_t tri_program, uint32_t proc_program, void *hits);
 

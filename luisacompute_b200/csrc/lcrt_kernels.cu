@@ -35,10 +35,9 @@ enum SmallSlots : uint32_t {
     SM_ROOT_HALF = 32 /* Bvh2Half of the root (12 words, 16-byte aligned) */,
     // the words every wide node touches, each on its own 128-byte line (they are served by one L2 slice each; sharing a
     // line with the polled flags made the counters' atomics queue behind the polls)
-    SM_COUNTERS = 64 /* nodes, prims, done prims at COUNTER_STRIDE words */, SM_DONE = 160 /* every wide node that is not deferred has been built */, SM_ABORT = 192,
-    SM_PENDING = 224 /* scheduled, not yet built wide nodes of the octet kernel */
+    SM_COUNTERS = 64 /* nodes, prims, done prims at COUNTER_STRIDE words */, SM_DONE = 160 /* every primitive has its record slot */, SM_ABORT = 192
 };
-static_assert(SM_COUNTERS + 2 * COUNTER_STRIDE < SM_DONE && SM_PENDING < SMALL_WORDS, "scratch words");
+static_assert(SM_COUNTERS + 2 * COUNTER_STRIDE < SM_DONE && SM_ABORT < SMALL_WORDS, "scratch words");
 static_assert(SM_ROOT_HALF * 4 % 16 == 0 && SM_ROOT_HALF + sizeof(Bvh2Half) / 4 <= SMALL_WORDS, "scratch words");
 
 __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t flags, BlobLayout L, uint32_t *small) {
@@ -55,7 +54,6 @@ __global__ void k_build_init(BlobHeader *h, uint32_t kind, uint32_t n, uint32_t 
         *h = hd;
         small[SM_CMIN + 0] = small[SM_CMIN + 1] = small[SM_CMIN + 2] = 0xffffffffu;
         small[SM_COUNTERS + 0 * COUNTER_STRIDE] = 1u;// the root
-        small[SM_PENDING] = 1u;
         if (n == 0u) {
             // an empty structure: one node with no children; nothing can be hit
             Node8 nd;
@@ -137,105 +135,26 @@ __global__ void __launch_bounds__(256) k_morton(const f4 *__restrict__ pbox, uin
     if (i < n) keys[i] = (morton63(box_from_pbox(pbox[2ull * i], pbox[2ull * i + 1]), clo, inv_ext, bits) << index_bits) | (uint64_t)i;
 }
 
-// The climb, block-local: a block owns CLIMB_CHUNK consecutive sorted leaves and keeps every binary node whose whole range
-// lies inside that chunk (99 % of them at any size) in SHARED memory — halves, arrival counters, shared-memory atomics — and
-// the thread that completes such a node writes its finished 96-byte record to global memory once.  Only nodes whose range
-// crosses a chunk boundary go through global memory and global atomics (lbvh_climb_from).  Which is which is decided
-// from the split levels alone (level(j) = highest bit in which sorted keys j and j + 1 differ; +inf outside the array):
-// node p, the split between leaves p and p + 1, spans the maximal interval around p whose other levels are smaller, so a
-// thread arriving from the left asks whether a larger level exists to the right of p inside the chunk (suffix maxima), one
-// arriving from the right whether one exists to the left (prefix maxima); both answers agree on "inside".
-constexpr int CLIMB_CHUNK = 256;
-struct ClimbSmem {
-    Bvh2Half l[CLIMB_CHUNK], r[CLIMB_CHUNK];// halves of node b0 + k
-    uint32_t flag[CLIMB_CHUNK];
-    uint8_t level[CLIMB_CHUNK + 1], premax[CLIMB_CHUNK + 1], sufmax[CLIMB_CHUNK + 1];// index k <-> split j = b0 - 1 + k
-};
-__global__ void __launch_bounds__(CLIMB_CHUNK) k_climb(Bvh2 t, const f4 *__restrict__ pbox) {
-    __shared__ ClimbSmem sm;
-    const uint32_t n = t.n, tid = threadIdx.x;
-    const uint32_t b0 = blockIdx.x * CLIMB_CHUNK, b1 = b0 + CLIMB_CHUNK < n ? b0 + CLIMB_CHUNK : n;// leaves [b0, b1)
-    // ---- split levels of j = b0 - 1 .. b1 - 1 (255 = outside the array), their prefix / suffix maxima
-    for (uint32_t k = tid; k <= (uint32_t)CLIMB_CHUNK; k += CLIMB_CHUNK) {
-        const long long j = (long long)b0 - 1 + k;
-        uint32_t lv = 255u;
-        if (j >= 0 && j + 1 < (long long)n && j <= (long long)b1 - 1) lv = 63u - (uint32_t)__clzll((long long)(t.keys[j] ^ t.keys[j + 1]));
-        if (j > (long long)b1 - 1) lv = 0u;// beyond this chunk's last split: not part of the maxima
-        sm.level[k] = (uint8_t)lv;
+// One thread per sorted leaf.  (Measured and rejected, profiles/r2_build_experiments.md: a block-local climb that keeps the nodes
+// whose range lies inside a 256-leaf chunk in shared memory and writes each finished record once: 151 -> 169 us.)
+__global__ void __launch_bounds__(64) k_climb(Bvh2 t, const f4 *__restrict__ pbox) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < t.n) {
+        const uint32_t p = t.order(i);
+        lbvh_climb(t, i, box_from_pbox(pbox[2ull * p], pbox[2ull * p + 1]));
     }
-    sm.flag[tid] = 0u;
-    __syncthreads();
-    if (tid < 32u) {
-        // 257 bytes: one warp, eight (nine) per lane, then a shuffle scan — twice (prefix, suffix)
-        const uint32_t cnt = b1 - b0 + 1u;// valid entries: k = 0 .. b1 - b0
-        uint32_t run = 0u;
-        const uint32_t per = (CLIMB_CHUNK + 1 + 31) / 32, k0 = tid * per;
-        for (uint32_t k = k0; k < k0 + per && k < cnt; k++) run = run > sm.level[k] ? run : sm.level[k];
-        uint32_t inc = run;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
-            if (tid >= (uint32_t)o) inc = inc > v ? inc : v;
-        }
-        uint32_t carry = __shfl_up_sync(0xffffffffu, inc, 1);
-        if (tid == 0u) carry = 0u;
-        for (uint32_t k = k0; k < k0 + per && k < cnt; k++) {
-            carry = carry > sm.level[k] ? carry : sm.level[k];
-            sm.premax[k] = (uint8_t)carry;
-        }
-        run = 0u;
-        for (uint32_t k = k0; k < k0 + per && k < cnt; k++) run = run > sm.level[k] ? run : sm.level[k];
-        inc = run;
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_down_sync(0xffffffffu, inc, o);
-            if (tid + (uint32_t)o < 32u) inc = inc > v ? inc : v;
-        }
-        carry = __shfl_down_sync(0xffffffffu, inc, 1);
-        if (tid == 31u) carry = 0u;
-        for (uint32_t kk = 0; kk < per; kk++) {
-            const uint32_t k = k0 + per - 1u - kk;
-            if (k >= cnt) continue;
-            carry = carry > sm.level[k] ? carry : sm.level[k];
-            sm.sufmax[k] = (uint8_t)carry;
-        }
-    }
-    __syncthreads();
-    const uint32_t i = b0 + tid;
-    if (i >= n) return;
-    uint32_t left = i, right = i;
-    const uint32_t prim = t.order(i);
-    Bvh2Half h = leaf_half(n, i, box_from_pbox(pbox[2ull * prim], pbox[2ull * prim + 1]));
-    for (;;) {
-        if (left == 0u && right == n - 1u) {
-            store_half(t.root, h);
-            return;
-        }
-        // the two candidate parents are splits right and left - 1, both inside this chunk's level table
-        const uint32_t lr = sm.level[right - b0 + 1u], ll = sm.level[left - b0];
-        const bool from_left = left == 0u || (right != n - 1u && lr < ll);
-        const uint32_t p = from_left ? right : left - 1u;
-        const uint32_t k = p - b0 + 1u;// index of split p in the tables (p >= b0 - 1)
-        bool local = p >= b0 && p + 1u <= b1 - 1u;
-        if (local) local = from_left ? sm.sufmax[k + 1u] > sm.level[k] : sm.premax[k - 1u] > sm.level[k];
-        if (!local) break;// this node's range crosses the chunk: global memory from here on
-        const uint32_t q = p - b0;
-        copy_vec16(from_left ? &sm.l[q] : &sm.r[q], &h, 3);
-        __threadfence_block();
-        if (atomicAdd(&sm.flag[q], 1u) == 0u) return;// the sibling (a thread of this block) will finish this node
-        __threadfence_block();
-        Bvh2Half s;
-        copy_vec16(&s, from_left ? &sm.r[q] : &sm.l[q], 3);
-        // the finished record goes out once: both halves
-        store_half(from_left ? &t.node[p].l : &t.node[p].r, h);
-        store_half(from_left ? &t.node[p].r : &t.node[p].l, s);
-        if (from_left) right = s.last;
-        else left = s.first;
-        merge_halves(t, h, s, p, left, right);
-    }
-    lbvh_climb_from(t, left, right, h);
 }
 
 #ifndef LCRT_COLLAPSE_MIN_BLOCKS
 #define LCRT_COLLAPSE_MIN_BLOCKS 8
+#endif
+#ifndef LCRT_COLLAPSE_SLEEP_AFTER
+#define LCRT_COLLAPSE_SLEEP_AFTER 16u
+#define LCRT_COLLAPSE_SLEEP_SHORT 32u
+#define LCRT_COLLAPSE_SLEEP_LONG 200u
+#endif
+#ifndef LCRT_COLLAPSE_PREFETCH
+#define LCRT_COLLAPSE_PREFETCH 0
 #endif
 constexpr int COLLAPSE_BLOCK = 128;
 
@@ -270,7 +189,7 @@ __device__ __forceinline__ void oct_set(OctChild &c, const Bvh2Half *src) {
 }
 // the record an opening of this child would read: asked for early, it is in L1 when the (sequential) opening loop gets there
 __device__ __forceinline__ void oct_prefetch(const Bvh2 &t, const OctChild &c) {
-    if (c.valid && !c.leaf) {
+    if (LCRT_COLLAPSE_PREFETCH && c.valid && !c.leaf) {
         const char *p = reinterpret_cast<const char *>(&t.node[c.id]);
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
         asm volatile("prefetch.global.L1 [%0];" ::"l"(p + 64));
@@ -293,14 +212,12 @@ __device__ __forceinline__ uint32_t oct_argmax(uint32_t key, uint32_t l, uint32_
 }
 __device__ __forceinline__ uint32_t oct_or(uint32_t v, uint32_t omask) { return __reduce_or_sync(omask, v); }
 
-constexpr uint32_t TASK_FITS = 0x80000000u;// task word y: the node's whole subtree fits into it (all children leaves): built by k_collapse_fits
-
-// SPLIT: children whose subtree fits into one node are only scheduled (flagged TASK_FITS) and left to k_collapse_fits, one
-// thread per node, after this kernel; `pending` counts the scheduled, not yet built nodes that are NOT deferred, and the
-// octet that brings it to zero raises `done`.
-template<class Input, bool NC, bool SPLIT>
+// COUNTED: the persistent kernel; the octet that hands out the last primitive slot raises `done`.  (Measured and rejected,
+// profiles/r2_build_experiments.md: leaving the six nodes out of seven whose whole subtree fits into one node to a second kernel
+// with one thread per node, 414 -> 337 + 195 us; counting pending nodes instead of primitives, two more fences per node.)
+template<class Input, bool NC, bool COUNTED>
 __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in, uint32_t widx, uint32_t bid, uint32_t depth, bool act,
-                               unsigned char *node_smem, uint32_t *done_flag, uint32_t *pending) {
+                               unsigned char *node_smem, uint32_t *done_flag) {
     const uint32_t l = threadIdx.x & 7u;
     OctChild c;
     c.id = INVALID_U32, c.valid = false, c.leaf = true, c.slots = 0u, c.count = 0u, c.first = 0u, c.area = 0.f;
@@ -416,12 +333,27 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
     const uint32_t cnt_by_slot = oct_or(is_leaf ? (c.count << (2 * slot)) : 0u, omask);// counts <= 3: two bits per slot
     const uint32_t n_int = (uint32_t)__popc(int_by_slot);
     const uint32_t n_prims = (uint32_t)__popc(cnt_by_slot & 0x5555u) + 2u * (uint32_t)__popc(cnt_by_slot & 0xaaaau);
-    uint32_t child_base = 0u, prim_base = 0u;
-    if (act && l == 0u) {
-        if (n_int) child_base = atomicAdd(&o.counters[0 * COUNTER_STRIDE], n_int);
-        if (n_prims) prim_base = atomicAdd(&o.counters[1 * COUNTER_STRIDE], n_prims);
+    // one atomic per WARP and counter: every wide node of the build goes through these two words, and same-address atomics are
+    // served one at a time by one L2 slice (the four octets of a warp add up first)
+    uint32_t child_base, prim_base, warp_prims;
+    {
+        const uint32_t oct = (threadIdx.x >> 3) & 3u, lane = threadIdx.x & 31u;
+        const uint32_t ai = act ? n_int : 0u, ap = act ? n_prims : 0u;
+        const uint32_t i0 = __shfl_sync(0xffffffffu, ai, 0), i1 = __shfl_sync(0xffffffffu, ai, 8), i2 = __shfl_sync(0xffffffffu, ai, 16),
+                       i3 = __shfl_sync(0xffffffffu, ai, 24);
+        const uint32_t p0 = __shfl_sync(0xffffffffu, ap, 0), p1 = __shfl_sync(0xffffffffu, ap, 8), p2 = __shfl_sync(0xffffffffu, ap, 16),
+                       p3 = __shfl_sync(0xffffffffu, ap, 24);
+        const uint32_t ti = i0 + i1 + i2 + i3, tpr = p0 + p1 + p2 + p3;
+        uint32_t bi = 0u, bp = 0u;
+        if (lane == 0u) {
+            if (ti) bi = atomicAdd(&o.counters[0 * COUNTER_STRIDE], ti);
+            if (tpr) bp = atomicAdd(&o.counters[1 * COUNTER_STRIDE], tpr);
+        }
+        bi = __shfl_sync(0xffffffffu, bi, 0), bp = __shfl_sync(0xffffffffu, bp, 0);
+        child_base = bi + (oct > 0u ? i0 : 0u) + (oct > 1u ? i1 : 0u) + (oct > 2u ? i2 : 0u);
+        prim_base = bp + (oct > 0u ? p0 : 0u) + (oct > 1u ? p1 : 0u) + (oct > 2u ? p2 : 0u);
+        warp_prims = tpr;
     }
-    child_base = __shfl_sync(0xffffffffu, child_base, 0, 8), prim_base = __shfl_sync(0xffffffffu, prim_base, 0, 8);
     bool ok = true;
     if (act && n_int && child_base + n_int > o.node_capacity) {
         if (l == 0u) o.header->error = 1u;
@@ -446,9 +378,8 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             const uint32_t w = child_base + (uint32_t)__popc(int_by_slot & ((1u << slot) - 1u));
             meta = (uint8_t)((1u << 5) | (24u + (uint32_t)slot));
             if (o.parent) o.parent[w] = (widx << 3) | (uint32_t)slot;
-            // one 64-bit store: a consumer that sees the node id also sees the depth (and whether the node is deferred)
-            const uint32_t fits = (SPLIT && c.slots <= 8u) ? TASK_FITS : 0u;
-            __stcg(reinterpret_cast<unsigned long long *>(&o.task[w]), ((unsigned long long)((depth + 1u) | fits) << 32) | c.id);
+            // one 64-bit store: a consumer that sees the node id also sees the depth
+            __stcg(reinterpret_cast<unsigned long long *>(&o.task[w]), ((unsigned long long)(depth + 1u) << 32) | c.id);
         } else {
             const uint32_t below = cnt_by_slot & ((1u << (2 * slot)) - 1u);
             const uint32_t po = (uint32_t)__popc(below & 0x5555u) + 2u * (uint32_t)__popc(below & 0xaaaau);
@@ -476,18 +407,14 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
             o.header->hi[0] = nhx, o.header->hi[1] = nhy, o.header->hi[2] = nhz;
             if (o.parent) o.parent[0] = INVALID_U32;
         }
-        if (n_prims) LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], n_prims);
     }
-    if constexpr (SPLIT) {
-        // this node is built; its children that are not deferred are now pending (their tasks were written above)
-        const uint32_t upper = oct_or((is_int && c.slots > 8u) ? (1u << l) : 0u, omask);
-        if (act && l == 0u) {
-            const uint32_t add = (uint32_t)__popc(upper);
+    __syncwarp();// the warp's node, task and parent stores precede the release below
+    if ((threadIdx.x & 31u) == 0u && warp_prims) {
+        const uint32_t before = LCRT_ATOMIC_ADD_ACQ_REL(&o.counters[2 * COUNTER_STRIDE], warp_prims);
+        if (COUNTED && before + warp_prims == t.n) {
+            // the last primitive has its slot: every wide node has been processed
             __threadfence();
-            if (atomicAdd(pending, add - 1u) + add - 1u == 0u) {
-                __threadfence();
-                *reinterpret_cast<volatile uint32_t *>(done_flag) = 1u;
-            }
+            *reinterpret_cast<volatile uint32_t *>(done_flag) = 1u;
         }
     }
     __syncwarp();
@@ -502,7 +429,7 @@ __device__ bool collapse_octet(const Bvh2 &t, const Bvh8Out &o, const Input &in,
 // never scheduled leave then.  (Round 1 ran level by level with a grid barrier per level: 0.58 ms at 1.3 M triangles.)
 template<class Input>
 __global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_collapse(Bvh2 t, Bvh8Out o, Input in, uint32_t *abort_flag, uint32_t *done_flag,
-                                                                                        uint32_t *levels_out, uint32_t *pending) {
+                                                                                        uint32_t *levels_out) {
     __shared__ __align__(16) unsigned char node_smem[(COLLAPSE_BLOCK / 8) * sizeof(Node8)];
     __shared__ uint32_t s_depth;
     if (threadIdx.x == 0) s_depth = 0u;
@@ -548,43 +475,16 @@ __global__ void __launch_bounds__(COLLAPSE_BLOCK, LCRT_COLLAPSE_MIN_BLOCKS) k_co
                     break;
                 }
             }
-            __nanosleep(idle < 8u ? 40u : idle < 32u ? 160u : idle < 128u ? 640u : 2000u);// back off: idle polls cost the busy warps issue slots
+            __nanosleep(idle < LCRT_COLLAPSE_SLEEP_AFTER ? LCRT_COLLAPSE_SLEEP_SHORT : LCRT_COLLAPSE_SLEEP_LONG);// back off: idle polls cost the busy warps issue slots
         }
         if (__all_sync(0xffffffffu, finished)) break;
         word = __shfl_sync(0xffffffffu, word, (int)(threadIdx.x & 24u));
-        const uint32_t bid = (uint32_t)word, depth = (uint32_t)(word >> 32) & ~TASK_FITS;
-        const bool deferred = act && ((uint32_t)(word >> 32) & TASK_FITS) != 0u && w != 0u;// k_collapse_fits builds it
-        const bool build = act && !deferred;
-        if (__any_sync(0xffffffffu, build)) {
-            if (!collapse_octet<Input, true, true>(t, o, in, w, bid, depth, build, node_smem, done_flag, pending)) atomicExch(abort_flag, 1u);
-        }
+        const uint32_t bid = (uint32_t)word, depth = (uint32_t)(word >> 32);
+        if (!collapse_octet<Input, true, true>(t, o, in, w, bid, depth, act, node_smem, done_flag)) atomicExch(abort_flag, 1u);
         if (act) {
-            if (l == 0u && build) atomicMax(&s_depth, depth);
+            if (l == 0u) atomicMax(&s_depth, depth);
             w += stride;
             if (w >= o.node_capacity) finished = true;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0 && s_depth) atomicMax(levels_out, s_depth);
-}
-
-// The deferred nodes (six out of seven): a subtree of at most eight leaf slots becomes one wide node whose children are all
-// leaves.  Nothing depends on them, so they are built after the octet kernel, ONE THREAD PER NODE over the whole index range
-// (collapse_node, the serial statement of the same decisions), with every SM full.
-template<class Input>
-__global__ void __launch_bounds__(128) k_collapse_fits(Bvh2 t, Bvh8Out o, Input in, const uint32_t *__restrict__ node_count, uint32_t *abort_flag,
-                                                        uint32_t *levels_out) {
-    __shared__ uint32_t s_depth;
-    if (threadIdx.x == 0) s_depth = 0u;
-    __syncthreads();
-    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t count = *node_count < o.node_capacity ? *node_count : o.node_capacity;
-    if (w != 0u && w < count) {
-        const u2 task = o.task[w];
-        if (task.x != INVALID_U32 && (task.y & TASK_FITS)) {
-            const uint32_t depth = task.y & ~TASK_FITS;
-            if (!collapse_node(t, o, in, w, task.x, depth)) atomicExch(abort_flag, 1u);
-            atomicMax(&s_depth, depth);
         }
     }
     __syncthreads();
@@ -681,7 +581,7 @@ __global__ void __launch_bounds__(SMALL_BLOCK) k_build_small(Input in, BlobHeade
             const bool act = w < end;
             uint32_t bid = INVALID_U32;
             if (act && w != 0u) bid = *reinterpret_cast<volatile uint32_t *>(&task[w].x);
-            if (!collapse_octet<Input, false, false>(t, o, in, w, bid, depth, act, node_smem, small + SM_DONE, small + SM_PENDING)) failed = true;
+            if (!collapse_octet<Input, false, false>(t, o, in, w, bid, depth, act, node_smem, small + SM_DONE)) failed = true;
         }
         __threadfence_block();
         __syncthreads();
@@ -876,6 +776,7 @@ __device__ __forceinline__ TraceSmem *trace_smem() {
 }
 struct HybridStore {
     static constexpr bool world_in_global = true;
+    static constexpr bool shareable = false;
     u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
     __device__ __forceinline__ void store(int i, u2 v) {
         if (i < TRACE_SMEM_STACK) trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] = v;
@@ -890,6 +791,18 @@ struct HybridStore {
     __device__ __forceinline__ uint32_t ldw(int k) const { return trace_smem()->words[k * TRACE_BLOCK + threadIdx.x]; }
 };
 
+// Where the final record of ray i goes: in place (dst == nullptr), or into a framebuffer of tiles — `tile` consecutive rays are
+// contiguous, tile j starts at dst + j * stride.  The framebuffer may be PEER memory (another GPU's HBM mapped over NVLink):
+// tile-sharded multi-GPU tracing writes its records straight into the gathering rank's ray-ordered buffer from this pass, so
+// there is no gather step and no reorder copy behind the trace (luisacompute_b200.dist.PeerFramebuffer).
+struct HitDest {
+    char *dst;
+    uint64_t tile, stride;
+    __device__ __forceinline__ u2 *at(void *in_place, uint64_t i) const {
+        if (dst == nullptr) return reinterpret_cast<u2 *>(static_cast<char *>(in_place) + i * 24u);
+        return reinterpret_cast<u2 *>(dst + (i / tile) * stride + (i % tile) * 24u);
+    }
+};
 struct TraceParams {
     const BlobHeader *tlas;
     const Instance *instances;
@@ -903,13 +816,18 @@ struct TraceParams {
     uint32_t tri_prog, proc_prog;
     int terminate_on_first;
     uint32_t magic;              // PLANT_MAGIC, see plant_byte()
+    HitDest dest;                // FUSED kernels: where the final records go
 };
 
 // Persistent threads: every warp reserves TRACE_BATCH consecutive rays per atomic and hands them to its idle lanes
 // (ballot + popc rank) whenever at least LCRT_REFILL_MIN lanes are idle; between refills every lane advances its
 // ray by one step() per iteration.  Surface hits are written in a provisional form (u = TLAS record index, prim =
 // primitive record index, t = fp32 distance) that k_refine_hits turns into the final record.
-template<int MODE, bool COUNT, class Callbacks>
+// FUSED (closest-hit only): the retiring lanes evaluate the exact record themselves and store it where HitDest says — a
+// framebuffer that may live in a peer GPU's memory.  The stores then leave over NVLink while the kernel is still tracing, spread
+// over its whole duration, instead of in one burst from a second pass (eight ranks storing into one at the same moment would
+// queue at its NVLink ingress).
+template<int MODE, bool COUNT, class Callbacks, bool FUSED = false>
 __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(TraceParams p) {
     HybridStore store;
     Callbacks cb;
@@ -940,7 +858,13 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                 // results are written here, together by all lanes that finished since the last refill
                 const uint64_t ray_idx = (uint64_t)(tr.world - p.rays);
                 const bool hit = tr.has_hit();
-                if constexpr (MODE == MODE_CLOSEST) {
+                if constexpr (MODE == MODE_CLOSEST && FUSED) {
+                    uint32_t prim = ~0u;
+                    float t = tr.hit_t(), u = 0.f, v = 0.f;
+                    if (hit) refine_surface_hit(tr.world, tlas_recs, tr.hit_rec(), tr.hit_pi(), prim, t, u, v);
+                    uint2 *o = reinterpret_cast<uint2 *>(p.dest.at(p.out, ray_idx));
+                    __stcs(o, make_uint2(tr.hit_inst(), prim)), __stcs(o + 1, make_uint2(as_uint(u), as_uint(v))), __stcs(o + 2, make_uint2(as_uint(t), 0u));
+                } else if constexpr (MODE == MODE_CLOSEST) {
                     u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
 #if LCRT_STREAM_HITS
                     __stcs(reinterpret_cast<uint2 *>(o), make_uint2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u));
@@ -1019,20 +943,27 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
 // Second pass of closest-hit / RayQuery batches: the reported (t, u, v) of every surface hit are recomputed in
 // double with the oracle's formula (refine_surface_hit), one thread per ray, fully convergent and coalesced.
 template<int MODE>
-__global__ void __launch_bounds__(256) k_refine_hits(const BlobHeader *tlas, const Ray *__restrict__ rays, void *out, uint64_t n) {
+__global__ void __launch_bounds__(256) k_refine_hits(const BlobHeader *tlas, const Ray *__restrict__ rays, void *out, uint64_t n, HitDest d) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const InstanceRecord *tlas_recs = reinterpret_cast<const InstanceRecord *>(reinterpret_cast<const char *>(tlas) + tlas->prims_offset);
-    u2 *o = reinterpret_cast<u2 *>(static_cast<char *>(out) + i * 24u);
-    const u2 h0 = o[0], h1 = o[1], h2 = o[2];
+    const u2 *in = reinterpret_cast<const u2 *>(static_cast<const char *>(out) + i * 24u);
+    u2 *o = d.at(out, i);
+    const u2 h0 = in[0], h1 = in[1], h2 = in[2];
     if constexpr (MODE == MODE_CLOSEST) {
-        if (h0.x == ~0u) return;
+        if (h0.x == ~0u) {
+            if (d.dst) o[0] = h0, o[1] = h1, o[2] = h2;// a miss is final as the trace wrote it
+            return;
+        }
         uint32_t prim = 0;
         float t = as_float(h2.x), u = 0.f, v = 0.f;
         refine_surface_hit(rays + i, tlas_recs, h1.x, h0.y, prim, t, u, v);
         o[0] = make_u2(h0.x, prim), o[1] = make_u2(as_uint(u), as_uint(v)), o[2] = make_u2(as_uint(t), 0u);
     } else {
-        if (h2.x != HIT_SURFACE) return;
+        if (h2.x != HIT_SURFACE) {
+            if (d.dst) o[0] = h0, o[1] = h1, o[2] = h2;
+            return;
+        }
         uint32_t prim = 0;
         float t = as_float(h2.y), u = 0.f, v = 0.f;
         refine_surface_hit(rays + i, tlas_recs, h1.x, h0.y, prim, t, u, v);
@@ -1145,7 +1076,8 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
     t.n = n, t.index_bits = index_bits, t.keys = sb.keys[cur];
     t.node = reinterpret_cast<Bvh2Node *>(tp + T.node);
     t.flag = flag, t.root = reinterpret_cast<Bvh2Half *>(small + SM_ROOT_HALF), t.ci = sah_ci(flags), t.max_leaf = Input::max_leaf;
-    k_climb<<<(n + CLIMB_CHUNK - 1u) / CLIMB_CHUNK, CLIMB_CHUNK, 0, stream>>>(t, pbox);
+    // 64-thread blocks: a block lives as long as its longest climber (most threads leave after one or two levels)
+    k_climb<<<(n + 63u) / 64u, 64, 0, stream>>>(t, pbox);
     LCRT_LAUNCH_CHECK("k_climb");
     Bvh8Out o;
     o.header = h, o.nodes = reinterpret_cast<Node8 *>(bp + L.nodes_offset), o.prims = bp + L.prims_offset;
@@ -1164,12 +1096,10 @@ static int build_generic(cudaStream_t stream, const Input &in, uint32_t flags, v
         const uint32_t need = (L.node_capacity + COLLAPSE_BLOCK / 8u - 1u) / (COLLAPSE_BLOCK / 8u);
         if (g > need) g = need;
         // cooperative launch: the runtime guarantees that all blocks are co-resident (octets wait for their parents' tasks)
-        uint32_t *abort_flag = small + SM_ABORT, *done_flag = small + SM_DONE, *levels = small + SM_LEVELS, *pending = small + SM_PENDING;
+        uint32_t *abort_flag = small + SM_ABORT, *done_flag = small + SM_DONE, *levels = small + SM_LEVELS;
         Input in_arg = in;
-        void *args[] = {&t, &o, &in_arg, &abort_flag, &done_flag, &levels, &pending};
+        void *args[] = {&t, &o, &in_arg, &abort_flag, &done_flag, &levels};
         LCRT_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(&k_collapse<Input>), dim3(g), dim3(COLLAPSE_BLOCK), args, 0, stream));
-        k_collapse_fits<Input><<<(L.node_capacity + 127u) / 128u, 128, 0, stream>>>(t, o, in, small + SM_COUNTERS, abort_flag, levels);
-        LCRT_LAUNCH_CHECK("k_collapse_fits");
     }
     k_emit_records<Input><<<blocks256, 256, 0, stream>>>(t, o, in, small + SM_CHILD_DEPTH);
     LCRT_LAUNCH_CHECK("k_emit_records");
@@ -1210,8 +1140,12 @@ static int refit_generic(cudaStream_t stream, const Input &in, void *temp, uint6
 
 template<int MODE, class Callbacks>
 static int trace_generic(cudaStream_t stream, const void *tlas, const void *instances, const void *rays, uint64_t n, const uint32_t *masks,
-                         uint32_t mask, void *out, uint64_t *counters, uint32_t tri_prog, uint32_t proc_prog, int terminate_on_first) {
+                         uint32_t mask, void *out, uint64_t *counters, uint32_t tri_prog, uint32_t proc_prog, int terminate_on_first,
+                         HitDest dest = HitDest{nullptr, 1u, 0u}) {
     if (n == 0) return LCRT_SUCCESS;
+    if (dest.dst != nullptr && (MODE == MODE_ANY || dest.tile == 0u || (reinterpret_cast<uintptr_t>(dest.dst) & 7u) || (dest.stride & 7u) ||
+                                dest.stride < dest.tile * 24u))
+        return LCRT_ERROR_INVALID_VALUE;
     if (tlas == nullptr || rays == nullptr || out == nullptr) return LCRT_ERROR_INVALID_VALUE;
     if (reinterpret_cast<uintptr_t>(rays) & 15u) return LCRT_ERROR_MISALIGNED;
     if (reinterpret_cast<uintptr_t>(out) & 7u) return LCRT_ERROR_MISALIGNED;
@@ -1224,21 +1158,28 @@ static int trace_generic(cudaStream_t stream, const void *tlas, const void *inst
     p.counters = reinterpret_cast<unsigned long long *>(counters);
     p.tri_prog = tri_prog, p.proc_prog = proc_prog, p.terminate_on_first = terminate_on_first, p.magic = PLANT_MAGIC;
     LCRT_CUDA(cudaMemsetAsync(p.next, 0, sizeof(unsigned long long), stream));
-    int bps = 0;
-    if (counters) {
-        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, true, Callbacks>, TRACE_BLOCK, sizeof(TraceSmem)));
-    } else {
-        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, k_trace<MODE, false, Callbacks>, TRACE_BLOCK, sizeof(TraceSmem)));
-    }
-    if (bps < 1) bps = 1;
-    uint64_t g = (uint64_t)dev->sm_count * (uint64_t)bps;
-    const uint64_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
-    if (g > need) g = need;
-    if (counters) k_trace<MODE, true, Callbacks><<<(uint32_t)g, TRACE_BLOCK, sizeof(TraceSmem), stream>>>(p);
-    else k_trace<MODE, false, Callbacks><<<(uint32_t)g, TRACE_BLOCK, sizeof(TraceSmem), stream>>>(p);
-    LCRT_LAUNCH_CHECK("k_trace");
-    if (MODE != MODE_ANY) {
-        k_refine_hits<MODE><<<(uint32_t)((n + 255u) / 256u), 256, 0, stream>>>(p.tlas, p.rays, out, n);
+    // closest-hit records that go to a tiled (possibly peer) framebuffer are finished inside the traversal kernel
+    static const bool force_fused = getenv("LCRT_FUSED_REFINE") != nullptr && atoi(getenv("LCRT_FUSED_REFINE")) != 0;
+    const bool fused = MODE == MODE_CLOSEST && counters == nullptr && (dest.dst != nullptr || force_fused);
+    p.dest = dest;
+    auto launch = [&](auto kernel) -> int {
+        int bps = 0;
+        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, TRACE_BLOCK, sizeof(TraceSmem)));
+        if (bps < 1) bps = 1;
+        uint64_t g = (uint64_t)dev->sm_count * (uint64_t)bps;
+        const uint64_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
+        if (g > need) g = need;
+        kernel<<<(uint32_t)g, TRACE_BLOCK, sizeof(TraceSmem), stream>>>(p);
+        LCRT_LAUNCH_CHECK("k_trace");
+        return LCRT_SUCCESS;
+    };
+    int rc;
+    if (counters) rc = launch(k_trace<MODE, true, Callbacks, false>);
+    else if (fused) rc = launch(k_trace<MODE, false, Callbacks, MODE == MODE_CLOSEST>);
+    else rc = launch(k_trace<MODE, false, Callbacks, false>);
+    if (rc != LCRT_SUCCESS) return rc;
+    if (MODE != MODE_ANY && !fused) {
+        k_refine_hits<MODE><<<(uint32_t)((n + 255u) / 256u), 256, 0, stream>>>(p.tlas, p.rays, out, n, dest);
         LCRT_LAUNCH_CHECK("k_refine_hits");
     }
     return LCRT_SUCCESS;
@@ -1363,6 +1304,13 @@ int lcrtTraceClosest(lcrtStream stream, const void *tlas, const void *instances,
                      uint32_t mask, void *hits, uint64_t *counters) {
     return trace_generic<MODE_CLOSEST, NoCallbacks>(static_cast<cudaStream_t>(stream), tlas, instances, rays, ray_count, masks, mask, hits, counters,
                                                     0, 0, 0);
+}
+
+int lcrtTraceClosestTiled(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                          uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays, uint64_t tile_stride_bytes, uint64_t *counters) {
+    if (dst == nullptr) return LCRT_ERROR_INVALID_VALUE;
+    return trace_generic<MODE_CLOSEST, NoCallbacks>(static_cast<cudaStream_t>(stream), tlas, instances, rays, ray_count, masks, mask, scratch_hits,
+                                                    counters, 0, 0, 0, HitDest{static_cast<char *>(dst), tile_rays, tile_stride_bytes});
 }
 
 int lcrtTraceAny(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,

@@ -138,3 +138,90 @@ class HitGatherer:
     def framebuffer(self):
         """[n_rays, words] in ray order (dst only)."""
         return None if self.full is None else self.full.view(-1, self.words)
+
+
+class _RawCudaBuffer:
+    """A device address as something torch.as_tensor understands (int32 view of `words` elements)."""
+
+    def __init__(self, address: int, words: int):
+        self.__cuda_array_interface__ = {"shape": (words,), "typestr": "<i4", "data": (address, False), "version": 3, "strides": None}
+
+
+class PeerFramebuffer:
+    """The gathering rank's ray-ordered framebuffer of 24-byte hit records, mapped into EVERY rank of the node so that each
+    rank's trace writes its tiles where ray order puts them (Accel.trace_closest_tiled -> lcrtTraceClosestTiled): the hit
+    gather of SURVEY.md 8e without a gather — the stores travel over NVLink while the rank is still tracing, rank `dst`
+    receives nothing it has to reorder, and the only collective left in a step is the completion barrier.
+
+    Layout: global tile j (`tile` consecutive rays) at byte j * tile * 24; local tile t of rank r is global tile
+    t * world + r, i.e. rank r writes with base = r * tile * 24 and stride = world * tile * 24.
+    `dst` allocates (lcbFramebufferCreate: cudaMalloc + CUDA IPC handle), the 64-byte handle is broadcast with
+    torch.distributed, the others map it (lcbFramebufferOpen, peer access enabled on first use).  Single-process use
+    (world 1) works the same without the exchange."""
+
+    def __init__(self, device, n_local_tiles: int, tile: int = TILE, dst: int = 0, words: int = 6):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _check, lib
+        self.device, self.tile, self.words, self.dst = device, tile, words, dst
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.n_local_tiles = n_local_tiles
+        self.bytes = n_local_tiles * self.world * tile * words * 4
+        self.owner = self.rank == dst
+        tdev = device.torch_device
+        handle = torch.zeros(64, dtype=torch.uint8, device=tdev)
+        addr = C.c_uint64(0)
+        if self.owner:
+            hb = (C.c_ubyte * 64)()
+            _check(lib().lcbFramebufferCreate(device._h, self.bytes, C.byref(addr), hb), "lcbFramebufferCreate")
+            handle.copy_(torch.frombuffer(bytearray(hb), dtype=torch.uint8))
+        if self.world > 1:
+            dist.broadcast(handle, dst)
+        if not self.owner:
+            hb = (C.c_ubyte * 64).from_buffer_copy(bytes(handle.cpu().numpy().tobytes()))
+            _check(lib().lcbFramebufferOpen(device._h, hb, C.byref(addr)), "lcbFramebufferOpen")
+        self.address = int(addr.value)
+        self.tile_bytes = tile * words * 4
+        self.base = self.address + self.rank * self.tile_bytes          # where this rank's local tile 0 goes
+        self.stride = self.world * self.tile_bytes
+        # the owner's view of the whole buffer, ray order
+        self.full = torch.as_tensor(_RawCudaBuffer(self.address, self.bytes // 4), device=tdev).view(-1, words) if self.owner else None
+
+    def trace_closest(self, accel, rays, mask=0xFF, scratch=None, first_local_tile: int = 0):
+        """Traces this rank's rays (local tiles first_local_tile ...) and stores the records into the framebuffer."""
+        return accel.trace_closest_tiled(rays, self.base + first_local_tile * self.stride, self.tile, self.stride, mask=mask, scratch=scratch)
+
+    def complete(self):
+        """Every rank's stores of the step are in the owner's memory once this returns on the owner's stream: kernel completion
+        makes them visible system-wide, the (tiny) all-reduce orders the owner's stream behind every rank's kernels."""
+        import torch
+        import torch.distributed as dist
+        if self.world > 1:
+            if not hasattr(self, "_token"):
+                self._token = torch.zeros(1, dtype=torch.int32, device=self.device.torch_device)
+            dist.all_reduce(self._token)
+
+    def close(self):
+        """Collective: the peers unmap, then the owner frees."""
+        import torch
+
+        from . import _check, lib
+        if not self.address:
+            return
+        torch.cuda.synchronize()
+        multi = self.world > 1
+        if multi:
+            import torch.distributed as dist
+            dist.barrier()          # nobody unmaps or frees while a peer may still be storing
+        self.full = None
+        if not self.owner:
+            _check(lib().lcbFramebufferClose(self.device._h, self.address), "lcbFramebufferClose")
+        if multi:
+            dist.barrier()          # every peer has unmapped
+        if self.owner:
+            _check(lib().lcbFramebufferDestroy(self.device._h, self.address), "lcbFramebufferDestroy")
+        self.address = 0

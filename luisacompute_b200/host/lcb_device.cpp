@@ -636,6 +636,58 @@ int lcbTraceClosest(lcbDevice *device, lcrtStream stream, uint64_t accel, const 
     return lcrtTraceClosest(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, hits, counters);
 }
 
+int lcbTraceClosestTiled(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
+                         uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays, uint64_t tile_stride_bytes, uint64_t *counters) {
+    LCB_DEVICE_GUARD(device);
+    auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
+    if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
+    device->note_stream(static_cast<cudaStream_t>(stream));
+    a->check_pending = true;
+    return lcrtTraceClosestTiled(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, scratch_hits, dst, tile_rays, tile_stride_bytes,
+                                 counters);
+}
+
+// ---- framebuffers shared between the processes of a node (one process per GPU): CUDA IPC over plain cudaMalloc memory
+int lcbFramebufferCreate(lcbDevice *device, uint64_t bytes, uint64_t *address, unsigned char handle[64]) {
+    LCB_DEVICE_GUARD(device);
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    if (!address || !handle || bytes == 0) return LCRT_ERROR_INVALID_VALUE;
+    void *p = nullptr;
+    LCB_CUDA(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        LCB_CUDA(e);
+    }
+    memcpy(handle, &h, 64);
+    *address = reinterpret_cast<uint64_t>(p);
+    return LCRT_SUCCESS;
+}
+
+int lcbFramebufferOpen(lcbDevice *device, const unsigned char handle[64], uint64_t *address) {
+    LCB_DEVICE_GUARD(device);
+    if (!address || !handle) return LCRT_ERROR_INVALID_VALUE;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    void *p = nullptr;
+    LCB_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *address = reinterpret_cast<uint64_t>(p);
+    return LCRT_SUCCESS;
+}
+
+int lcbFramebufferClose(lcbDevice *device, uint64_t address) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaIpcCloseMemHandle(reinterpret_cast<void *>(address)));
+    return LCRT_SUCCESS;
+}
+
+int lcbFramebufferDestroy(lcbDevice *device, uint64_t address) {
+    LCB_DEVICE_GUARD(device);
+    LCB_CUDA(cudaFree(reinterpret_cast<void *>(address)));
+    return LCRT_SUCCESS;
+}
+
 int lcbTraceAny(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
                 uint32_t mask, uint32_t *occluded, uint64_t *counters) {
     LCB_DEVICE_GUARD(device);

@@ -34,6 +34,20 @@ extern "C" __global__ void k_devlib_trace(Params params) {
     static_cast<lc_uint *>(params.out1)[i] = lc_accel_trace_any(params.accel, ray, params.mask) ? 1u : 0u;
 }
 
+// closest-hit only / any-hit only (tools/devlib_perf.py times them)
+extern "C" __global__ void k_devlib_closest(Params params) {
+    const lc_uint i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= params.n) return;
+    LCRay ray = params.rays[i];
+    static_cast<LCTriangleHit *>(params.out0)[i] = lc_accel_trace_closest(params.accel, ray, params.mask);
+}
+extern "C" __global__ void k_devlib_any(Params params) {
+    const lc_uint i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= params.n) return;
+    LCRay ray = params.rays[i];
+    static_cast<lc_uint *>(params.out1)[i] = lc_accel_trace_any(params.accel, ray, params.mask) ? 1u : 0u;
+}
+
 // ---- RayQuery site #0: outlined handlers as emitted by RayQueryLowering::_create_outline_definitions
 struct LCRayQueryCtx0 {
     LCAccel accel;
@@ -144,6 +158,16 @@ static Params make_params(uint64_t handle, void *instances, const void *rays, ui
 DL_EXPORT int dl_trace(void *stream, uint64_t handle, void *instances, const void *rays, uint32_t n, uint32_t mask, void *hits, void *occluded) {
     if (n == 0) return 0;
     k_devlib_trace<<<(n + 127u) / 128u, 128, 0, static_cast<cudaStream_t>(stream)>>>(make_params(handle, instances, rays, n, mask, hits, occluded, nullptr, 0));
+    return (int)cudaGetLastError();
+}
+DL_EXPORT int dl_closest(void *stream, uint64_t handle, void *instances, const void *rays, uint32_t n, uint32_t mask, void *hits, uint32_t block) {
+    if (n == 0) return 0;
+    k_devlib_closest<<<(n + block - 1u) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(make_params(handle, instances, rays, n, mask, hits, nullptr, nullptr, 0));
+    return (int)cudaGetLastError();
+}
+DL_EXPORT int dl_any(void *stream, uint64_t handle, void *instances, const void *rays, uint32_t n, uint32_t mask, void *occluded, uint32_t block) {
+    if (n == 0) return 0;
+    k_devlib_any<<<(n + block - 1u) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(make_params(handle, instances, rays, n, mask, nullptr, occluded, nullptr, 0));
     return (int)cudaGetLastError();
 }
 DL_EXPORT int dl_query(void *stream, uint64_t handle, void *instances, const void *rays, uint32_t n, uint32_t mask, const void *aabbs, uint32_t tri_prog,
