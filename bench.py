@@ -211,7 +211,7 @@ def make_peer_framebuffer(dev, n_local_tiles: int):
     import torch.distributed as dist
     from luisacompute_b200.dist import PeerFramebuffer
     ok, fb = 1, None
-    if os.environ.get("LCB_GATHER", "peer") != "peer":
+    if gather_mode() == "nccl":
         ok = 0
     else:
         try:
@@ -228,10 +228,26 @@ def make_peer_framebuffer(dev, n_local_tiles: int):
     return fb
 
 
+def gather_mode() -> str:
+    """stores (default): the trace kernel itself stores its finished records into rank 0's mapped framebuffer; dma: traced chunk
+    by chunk, each chunk's records copied there by the copy engines while the next chunk is traced (the chunked launches cost
+    more than the copies hide: profiles/r2_scaling.md); nccl: send / recv + reorder copy."""
+    m = os.environ.get("LCB_GATHER", "stores")
+    return m if m in ("dma", "stores", "nccl") else "stores"
+
+
+DMA_CHUNK_TILES = int(os.environ.get("LCB_GATHER_CHUNK_TILES", "16"))
+
+
 def gather_description(fb, gat) -> str:
+    if fb is not None and gather_mode() == "dma":
+        return (f"peer framebuffer, copy engines: rank 0's ray-ordered buffer is mapped into every rank (CUDA IPC); each {DMA_CHUNK_TILES}-tile chunk's "
+                "24-byte records go there with one strided device-to-device copy over NVLink on a side stream while the next chunk is traced "
+                "(lcbFramebufferCopyTiles); one completion all-reduce per step, no gather collective, no reorder copy")
     if fb is not None:
-        return ("peer framebuffer: every rank's refine pass stores its 24-byte records straight into rank 0's ray-ordered buffer over NVLink "
-                "(CUDA IPC mapping, lcrtTraceClosestTiled); one completion all-reduce per step, no gather collective, no reorder copy")
+        how = ("one by one as the rays end" if fb.world <= 2 else "the records of each 128-ray batch together when the batch is complete (512-byte warp stores)")
+        return ("peer framebuffer, stores: every rank's trace kernel stores its finished 24-byte records straight into rank 0's ray-ordered buffer over "
+                f"NVLink, {how} (CUDA IPC mapping, lcrtTraceClosestTiled); one completion all-reduce per step, no gather collective, no reorder copy")
     if gat is not None:
         return "NCCL send / recv of 24-byte records, chunk by chunk on a side stream, one strided reorder copy per chunk (HitGatherer)"
     return "single GPU"
@@ -319,9 +335,18 @@ def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
     ct = 2 * CHUNK_TILES
 
     def step():
-        if fb is not None:
-            # one launch; the refine pass stores every record into rank 0's ray-ordered framebuffer over NVLink
+        if fb is not None and gather_mode() == "stores":
+            # one launch; the kernel stores every finished record into rank 0's ray-ordered framebuffer over NVLink
             fb.trace_closest(acc, lb, scratch=hits)
+            fb.complete()
+            return
+        if fb is not None:
+            for t0 in range(0, n_tiles_local, DMA_CHUNK_TILES):
+                t1 = min(t0 + DMA_CHUNK_TILES, n_tiles_local)
+                acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
+                ev = torch.cuda.Event()
+                ev.record()
+                fb.submit(hits[t0 * TILE:t1 * TILE], t0, ev)
             fb.complete()
             return
         if gat is None:
@@ -347,12 +372,10 @@ def c4_strong(args, lc, dev, world: int, rank: int, barrier) -> dict:
     # the trace alone (records stay on this rank)
     t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0e.record()
-    if gat is None:
-        acc.trace_closest(lb, out=hits)
-    else:
-        for t0 in range(0, n_tiles_local, ct):
-            t1 = min(t0 + ct, n_tiles_local)
-            acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
+    tct = n_tiles_local if (gat is None and (fb is None or gather_mode() == "stores")) else (ct if gat is not None else DMA_CHUNK_TILES)
+    for t0 in range(0, n_tiles_local, tct):
+        t1 = min(t0 + tct, n_tiles_local)
+        acc.trace_closest(lb[t0 * TILE * 32:t1 * TILE * 32], out=hits[t0 * TILE:t1 * TILE])
     t1e.record()
     torch.cuda.synchronize()
     trace_ms = t0e.elapsed_time(t1e)
@@ -545,8 +568,17 @@ def main():
         if gat is None:
             acc.trace_closest(d_rays, out=d_hits)
             return
-        if fb_p is not None:
+        if fb_p is not None and gather_mode() == "stores":
             (fb_p if gat is gat_p else fb_b).trace_closest(acc, d_rays, scratch=d_scr)
+            return
+        if fb_p is not None:
+            fb = fb_p if gat is gat_p else fb_b
+            for t0 in range(0, n_tiles, DMA_CHUNK_TILES):
+                t1 = min(t0 + DMA_CHUNK_TILES, n_tiles)
+                acc.trace_closest(d_rays[t0 * TILE * 32:t1 * TILE * 32], out=d_hits[t0 * TILE:t1 * TILE])
+                e = torch.cuda.Event()
+                e.record()
+                fb.submit(d_hits[t0 * TILE:t1 * TILE], t0, e)
             return
         for t0 in range(0, n_tiles, CHUNK_TILES):
             t1 = min(t0 + CHUNK_TILES, n_tiles)
@@ -557,7 +589,9 @@ def main():
 
     def end_step():
         if fb_p is not None:
-            fb_b.complete()     # one all-reduce orders rank 0's stream behind every rank's launches of the step
+            if gather_mode() == "dma":
+                fb_p.complete_local()
+            fb_b.complete()     # one all-reduce orders rank 0's stream behind every rank's launches and copies of the step
         elif gat_p is not None:
             gat_p.finish(), gat_b.finish()
 
@@ -768,7 +802,7 @@ def main():
                        "scene_gen_s": gen_s},
             "roofline": roofline, "roofline_build": roofline_build, "cpu_baseline": cpu, "reference_gpu": ref_gpu, "dropin_backend": dropin, "e2e": e2e, "clocks": clocks,
             # per step: k_trace + k_refine_hits per launch; one launch per batch at N = 1, one per CHUNK_TILES tiles otherwise
-            "gpu_launches": 4 * K if (world == 1 or gather_text.startswith("peer")) else 4 * K * ((n_tiles + CHUNK_TILES - 1) // CHUNK_TILES),
+            "gpu_launches": 4 * K if (world == 1 or gather_text.startswith("peer framebuffer, stores")) else 4 * K * ((n_tiles + DMA_CHUNK_TILES - 1) // DMA_CHUNK_TILES) if gather_text.startswith("peer") else 4 * K * ((n_tiles + CHUNK_TILES - 1) // CHUNK_TILES),
         }
         print(json.dumps(line))
     if fb_p is not None:

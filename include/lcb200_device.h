@@ -101,7 +101,7 @@ LCRT_API int lcbTraceAny(lcbDevice *device, lcrtStream stream, uint64_t accel, c
 /* lcbTraceClosest with the records written into a tiled framebuffer, possibly in a peer GPU's memory (lcrtTraceClosestTiled) */
 LCRT_API int lcbTraceClosestTiled(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count,
                                   const uint32_t *masks, uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays,
-                                  uint64_t tile_stride_bytes, uint64_t *counters);
+                                  uint64_t tile_stride_bytes, uint32_t flags, uint64_t *counters);
 /* A framebuffer other processes of this node can write into (one process per GPU): Create allocates `bytes` on
  * this device and fills the 64-byte handle the owner hands to its peers (any channel: a torch.distributed broadcast, a
  * file); Open maps it into the calling process (peer access over NVLink / PCIe is enabled on first use) and returns the
@@ -109,6 +109,11 @@ LCRT_API int lcbTraceClosestTiled(lcbDevice *device, lcrtStream stream, uint64_t
 LCRT_API int lcbFramebufferCreate(lcbDevice *device, uint64_t bytes, uint64_t *address, unsigned char handle[64]);
 LCRT_API int lcbFramebufferOpen(lcbDevice *device, const unsigned char handle[64], uint64_t *address);
 LCRT_API int lcbFramebufferClose(lcbDevice *device, uint64_t address);
+/* `tile_count` tiles of `tile_bytes` each, contiguous at `src` on this device, to dst + j * dst_stride_bytes (j = 0 ..): one
+ * strided device-to-device copy on `stream`, done by the copy engines — over NVLink when dst is a peer's framebuffer — so it
+ * overlaps with kernels of other streams without taking SMs from them. */
+LCRT_API int lcbFramebufferCopyTiles(lcbDevice *device, lcrtStream stream, const void *src, uint64_t dst, uint64_t tile_bytes,
+                                     uint64_t dst_stride_bytes, uint64_t tile_count);
 LCRT_API int lcbFramebufferDestroy(lcbDevice *device, uint64_t address);
 LCRT_API int lcbQuery(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
                       uint32_t mask, int terminate_on_first, uint32_t tri_program, uint32_t proc_program, void *hits);

@@ -115,13 +115,17 @@ LCRT_API int lcrtTraceClosest(lcrtStream stream, const void *tlas, const void *i
 LCRT_API int lcrtTraceAny(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count,
                           const uint32_t *masks, uint32_t mask, uint32_t *occluded, uint64_t *counters);
 /* lcrtTraceClosest whose final records go into a framebuffer of tiles instead of hits[]: ray i -> dst + (i / tile_rays) *
- * tile_stride_bytes + (i % tile_rays) * 24.  scratch_hits: SurfaceHit[ray_count] on this device (the traversal's provisional
+ * tile_stride_bytes + (i % tile_rays) * 24 (tile_rays a multiple of 128).  scratch_hits: SurfaceHit[ray_count] on this device (the traversal's provisional
  * records).  dst may be another GPU's memory mapped into this process (lcbFramebufferOpen): tile-sharded multi-GPU tracing
  *  writes straight into the gathering rank's ray-ordered framebuffer over NVLink from the same launches, with no
- * gather collective and no reorder copy behind the trace.  Nothing like it exists in the reference (no multi-GPU path at all). */
+ * gather collective and no reorder copy behind the trace.  Nothing like it exists in the reference (no multi-GPU path at all).
+ * flags: 0 = the records of each 128-ray batch are collected (in scratch_hits) and stored together when the batch is complete
+ * (512-byte warp stores: what a peer's NVLink ingress handles well when several GPUs write into one);
+ * LCRT_TILED_STORE_EACH_RECORD = every record is stored on its own when its ray ends (less work per ray; fine for one or two writers). */
+#define LCRT_TILED_STORE_EACH_RECORD 1u
 LCRT_API int lcrtTraceClosestTiled(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count,
                                    const uint32_t *masks, uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays,
-                                   uint64_t tile_stride_bytes, uint64_t *counters);
+                                   uint64_t tile_stride_bytes, uint32_t flags, uint64_t *counters);
 /* RayQuery (query_all, or query_any if terminate_on_first) with fixed candidate programs; hits: CommittedHit[ray_count] */
 LCRT_API int lcrtQuery(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count,
                        const uint32_t *masks, uint32_t mask, int terminate_on_first, uint32_t tri_program,

@@ -91,7 +91,7 @@ ABI_SYMBOLS = [
     "lcbAccelBuild", "lcbAccelGetBinding", "lcbLastBuildKind", "lcbNativeHandle", "lcbBlobInfo", "lcbTraceClosest", "lcbTraceAny",
     "lcbQuery", "lcbTraceClosestHost", "lcbSynchronize", "lcbDownload", "lcbUpload",
     "lcbPrimitiveExport", "lcbPrimitiveImport",
-    "lcbTraceClosestTiled", "lcbFramebufferCreate", "lcbFramebufferOpen", "lcbFramebufferClose", "lcbFramebufferDestroy",
+    "lcbTraceClosestTiled", "lcbFramebufferCreate", "lcbFramebufferOpen", "lcbFramebufferClose", "lcbFramebufferDestroy", "lcbFramebufferCopyTiles",
     # plumbing used by the backend plugin (plugin/lc_backend_b200rt.cpp)
     "lcbDeviceCount", "lcbDeviceName", "lcbBufferCreate", "lcbBufferDestroy", "lcbStreamCreate", "lcbStreamDestroy", "lcbCopyAsync",
     "lcbHostCallback", "lcbEventCreate", "lcbEventDestroy", "lcbEventSignal", "lcbEventWait", "lcbEventSynchronize", "lcbEventIsCompleted",
@@ -152,12 +152,13 @@ def lib():
     L.lcbTraceClosest.argtypes = [vp, vp, u64, vp, u64, vp, u32, vp, vp]
     L.lcbTraceAny.argtypes = [vp, vp, u64, vp, u64, vp, u32, vp, vp]
     L.lcbQuery.argtypes = [vp, vp, u64, vp, u64, vp, u32, i32, u32, u32, vp]
-    L.lcrtTraceClosestTiled.argtypes = [vp, vp, vp, vp, u64, vp, u32, vp, vp, u64, u64, vp]
-    L.lcbTraceClosestTiled.argtypes = [vp, vp, u64, vp, u64, vp, u32, vp, vp, u64, u64, vp]
+    L.lcrtTraceClosestTiled.argtypes = [vp, vp, vp, vp, u64, vp, u32, vp, vp, u64, u64, u32, vp]
+    L.lcbTraceClosestTiled.argtypes = [vp, vp, u64, vp, u64, vp, u32, vp, vp, u64, u64, u32, vp]
     L.lcbFramebufferCreate.argtypes = [vp, u64, C.POINTER(u64), vp]
     L.lcbFramebufferOpen.argtypes = [vp, vp, C.POINTER(u64)]
     L.lcbFramebufferClose.argtypes = [vp, u64]
     L.lcbFramebufferDestroy.argtypes = [vp, u64]
+    L.lcbFramebufferCopyTiles.argtypes = [vp, vp, vp, u64, u64, u64, u64]
     L.lcbTraceClosestHost.argtypes = [vp, u64, vp, u64, u32, vp, u64]
     L.lcbSynchronize.argtypes = [vp, vp]
     L.lcbDownload.argtypes = [vp, vp, u64, vp, u64]
@@ -506,17 +507,20 @@ class Accel(_Resource):
                                      counters.data_ptr() if counters is not None else None), "lcbTraceClosest")
         return out
 
-    def trace_closest_tiled(self, rays, dst_address: int, tile_rays: int, tile_stride_bytes: int, mask=0xFF, scratch=None, counters=None):
+    def trace_closest_tiled(self, rays, dst_address: int, tile_rays: int, tile_stride_bytes: int, mask=0xFF, scratch=None, counters=None,
+                            store_each_record: bool = False):
         """trace_closest whose final records go to dst_address + (i // tile_rays) * tile_stride_bytes + (i % tile_rays) * 24
         (a framebuffer of tiles, possibly in a peer GPU's memory: luisacompute_b200.dist.PeerFramebuffer).  `scratch`: int32
-        [n, 6] on this device for the traversal's provisional records (allocated if None)."""
+        [n, 6] on this device where the records of a 128-ray batch wait until the batch is complete (allocated if None);
+        store_each_record: every record goes out on its own when its ray ends (LCRT_TILED_STORE_EACH_RECORD)."""
         import torch
         r, n = self._rays(rays)
         mp, mv, keep = self._masks(mask)
         if scratch is None:
             scratch = torch.empty((n, 6), dtype=torch.int32, device=self.device.torch_device)
         _check(lib().lcbTraceClosestTiled(self.device._h, _stream(), self.handle, r.data_ptr(), n, mp, mv, scratch.data_ptr(), dst_address,
-                                          tile_rays, tile_stride_bytes, counters.data_ptr() if counters is not None else None),
+                                          tile_rays, tile_stride_bytes, 1 if store_each_record else 0,
+                                          counters.data_ptr() if counters is not None else None),
                "lcbTraceClosestTiled")
         return scratch
 

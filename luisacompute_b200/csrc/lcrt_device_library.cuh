@@ -193,179 +193,7 @@ __device__ inline void devlib_report(LCAccel accel, bool overflowed) noexcept {
 }
 }// namespace lcrt
 
-// ---- closest / any-hit for generated kernels: one thread, one ray — and idle lanes that help.
-// A generated kernel calls lc_accel_trace_closest per thread; the warp leaves the call when its LONGEST ray is done, and
-// on incoherent rays most lanes spend most of that time idle (the batch kernels refill idle lanes with new rays; a
-// generated kernel has none to give).  Here an idle lane takes over the OLDEST pending subtree of a busy lane's traversal
-// stack — the entry at the bottom, the farthest and usually largest piece of work that ray still has — together with the
-// ray, traverses it on its own stack, and reports what it found to the lane that owns the ray:
-//   * every lane keeps the result of ITS ray apart from the traversal it happens to be running (SharedBest): exact distance
-//     (double, the oracle's formula), barycentrics, ids.  A finished (sub)traversal evaluates its best hit exactly with the
-//     ray it holds and hands it to the owner, who keeps the smaller distance, ties to the lower (instance, primitive) —
-//     the rule the single-lane traversal applies, so the result does not depend on who traversed what;
-//   * a reported hit also shrinks the culling distance of every lane still working on that ray (any-hit: ends them);
-//   * entries are given away from the bottom of the stack (Traversal::bottom), so the donor's own order — near subtrees
-//     first — is untouched; an entry below the instance boundary restarts in the TLAS with the world ray, one above it
-//     carries the donor's object-space ray, shear rows and instance context (24 more shuffles).
-// All exchanges are warp shuffles between the lanes that entered the call together; nothing is shared through memory.
-#ifndef LCRT_TRACE_SHARED
-#define LCRT_TRACE_SHARED 1
-#endif
-#ifndef LCRT_SHARE_PERIOD
-#define LCRT_SHARE_PERIOD 4    // iterations between two attempts to pair idle lanes with donors
-#endif
-#ifndef LCRT_SHARE_MIN_ENTRIES
-#define LCRT_SHARE_MIN_ENTRIES 1// stack entries a lane must have pending to give its oldest one away
-#endif
-namespace lcrt {
-struct SharedBest {
-    double td;
-    float u, v;
-    uint32_t inst, prim;
-    bool hit;
-};
-__device__ inline double devlib_shfl_f64(uint32_t group, double x, int src) noexcept {
-    const int hi = __shfl_sync(group, __double2hiint(x), src), lo = __shfl_sync(group, __double2loint(x), src);
-    return __hiloint2double(hi, lo);
-}
-__device__ inline float devlib_shfl_f32(uint32_t group, float x, int src) noexcept { return __shfl_sync(group, x, src); }
-
-template<int MODE>
-__device__ __noinline__ void trace_shared(const BlobHeader *tlas, const Instance *instances, const Ray *own_ray, uint32_t mask, SharedBest *out,
-                                          bool *overflowed) noexcept {
-    using T = Traversal<MODE, false, SharedLocalStore, NoCallbacks>;
-    SharedLocalStore store;
-    NoCallbacks cb;
-    T tr;
-    Ray cur = *own_ray;// the ray this lane is working on: its own first, other lanes' later
-    tr.init(tlas, instances, &cur, mask, &store, &cb);
-    *overflowed = tr.overflowed();
-    const uint32_t group = __activemask();
-    uint32_t lane;
-    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t owner = lane;
-    SharedBest best;
-    best.hit = false, best.td = 0.0, best.u = best.v = 0.f, best.inst = best.prim = ~0u;
-    bool task = !tr.done;// this lane is running a (sub)traversal
-    for (uint32_t iter = 0u;; iter++) {
-        // ---- 1. (sub)traversals that just ended report their best hit to the lane that owns the ray
-        const bool fin = task && tr.done;
-        bool c_hit = false;
-        double c_td = 0.0;
-        float c_u = 0.f, c_v = 0.f;
-        uint32_t c_inst = ~0u, c_prim = ~0u;
-        if (fin) {
-            task = false;
-            if (tr.has_hit()) {
-                c_hit = true, c_inst = tr.hit_inst();
-                if (MODE == MODE_CLOSEST) {
-                    const InstanceRecord *r = tr.tlas_recs + tr.hit_rec();
-                    const f4 *tri = reinterpret_cast<const f4 *>(reinterpret_cast<const char *>(r->prims) + (uint64_t)tr.hit_pi() * sizeof(TriRecord));
-                    c_prim = as_uint(tri[0].w);
-                    if (!tri_exact_world(&cur, r, tri, c_td, c_u, c_v)) c_td = (double)tr.hit_t(), c_u = c_v = 0.f;// (the fp32 bounds exclude this)
-                }
-            }
-        }
-        uint32_t fm = __ballot_sync(group, fin && c_hit);
-        while (fm) {
-            const int h = __ffs((int)fm) - 1;
-            fm &= fm - 1u;
-            const uint32_t o = __shfl_sync(group, owner, h);
-            if (MODE == MODE_ANY) {
-                if (lane == o) best.hit = true;
-                if (task && owner == o) tr.done = true, task = false;// any hit ends every lane working on that ray
-            } else {
-                const double td = devlib_shfl_f64(group, c_td, h);
-                const float u = devlib_shfl_f32(group, c_u, h), v = devlib_shfl_f32(group, c_v, h);
-                const uint32_t inst = __shfl_sync(group, c_inst, h), prim = __shfl_sync(group, c_prim, h);
-                if (lane == o && (!best.hit || td < best.td || (td == best.td && (inst < best.inst || (inst == best.inst && prim < best.prim)))))
-                    best.hit = true, best.td = td, best.u = u, best.v = v, best.inst = inst, best.prim = prim;
-                if (task && owner == o) {
-                    const float t = (float)td;
-                    tr.tmax = fminf(tr.tmax, fmaf(fabsf(t), 3.6e-7f, t));// as Traversal::accept: a hair beyond, exact ties must still be visited
-                }
-            }
-        }
-        // ---- 2. done when nobody is running anything
-        const uint32_t busy = __ballot_sync(group, task);
-        if (busy == 0u) break;
-        // ---- 3. idle lanes take the oldest pending subtree of busy lanes
-        const uint32_t idle = group & ~busy;
-        if (idle != 0u && (iter % (uint32_t)LCRT_SHARE_PERIOD) == 0u) {
-            const bool can_give = task && !tr.done && tr.sp - tr.bottom >= LCRT_SHARE_MIN_ENTRIES;
-            const uint32_t donors = __ballot_sync(group, can_give);
-            if (donors != 0u) {
-                const int pairs = min(__popc(idle), __popc(donors));
-                const int rank = task ? __popc(donors & lt) : __popc(idle & lt);
-                const bool taker = !task && rank < pairs, giver = can_give && rank < pairs;
-                const int src = taker ? (int)__fns(donors, 0u, rank + 1) : (int)lane;
-                u2 e = make_u2(0u, 0u);
-                uint32_t in_tlas = 1u;
-                if (giver) {
-                    e = store.load(tr.bottom);
-                    in_tlas = (tr.blas_sp < 0 || tr.bottom < tr.blas_sp) ? 1u : 0u;
-                    tr.bottom++;
-                }
-                e.x = __shfl_sync(group, e.x, src), e.y = __shfl_sync(group, e.y, src);
-                in_tlas = __shfl_sync(group, in_tlas, src);
-                const uint32_t n_owner = __shfl_sync(group, owner, src), n_mask = __shfl_sync(group, tr.ray_mask, src);
-                const float n_tmax = devlib_shfl_f32(group, tr.tmax, src);
-                Ray nr;
-                nr.ox = devlib_shfl_f32(group, cur.ox, src), nr.oy = devlib_shfl_f32(group, cur.oy, src), nr.oz = devlib_shfl_f32(group, cur.oz, src);
-                nr.tmin = devlib_shfl_f32(group, cur.tmin, src), nr.dx = devlib_shfl_f32(group, cur.dx, src), nr.dy = devlib_shfl_f32(group, cur.dy, src);
-                nr.dz = devlib_shfl_f32(group, cur.dz, src), nr.tmax = devlib_shfl_f32(group, cur.tmax, src);
-                if (taker) {
-                    cur = nr, owner = n_owner, task = true;
-                    tr.tmin = nr.tmin, tr.tmax = n_tmax, tr.ray_mask = n_mask;
-                    tr.sp = 0, tr.bottom = 0, tr.tp = 0u, tr.done = false;
-                    if (e.y & 0xff000000u) tr.G = e, tr.Gt = make_u2(0u, 0u);
-                    else tr.Gt = e, tr.G = make_u2(0u, 0u);
-                    store.stw(CW_HIT_T, as_uint(nr.tmax)), store.stw(CW_HIT_TERR, as_uint(-1.0f));
-                    store.stw(CW_HIT_INST, ~0u), store.stw(CW_HIT_PRIM, ~0u), store.stw(CW_HIT_TYPE, HIT_MISS), store.stw(CW_HIT_EXACT, 0u);
-                    // a TLAS entry: the world ray is set up when the first node needs it
-                    tr.blas_sp = -1, tr.nodes = tr.tlas_nodes, tr.prims = reinterpret_cast<const char *>(tr.tlas_recs);
-                    tr.cur_inst = ~0u, tr.cur_flags = 0u, tr.octinv = T::RAY_PENDING;
-                    store.stw(CW_REC, 0u);
-                }
-                if (__any_sync(group, taker && in_tlas == 0u)) {
-                    // an entry inside an instance: the giver's object-space ray and instance context come along
-                    const float b_ox = devlib_shfl_f32(group, tr.ox, src), b_oy = devlib_shfl_f32(group, tr.oy, src), b_oz = devlib_shfl_f32(group, tr.oz, src);
-                    const float b_ix = devlib_shfl_f32(group, tr.idx, src), b_iy = devlib_shfl_f32(group, tr.idy, src), b_iz = devlib_shfl_f32(group, tr.idz, src);
-                    const uint32_t b_oct = __shfl_sync(group, tr.octinv, src), b_inst = __shfl_sync(group, tr.cur_inst, src), b_flags = __shfl_sync(group, tr.cur_flags, src);
-                    const unsigned long long b_nodes = __shfl_sync(group, (unsigned long long)reinterpret_cast<uintptr_t>(tr.nodes), src);
-                    const unsigned long long b_prims = __shfl_sync(group, (unsigned long long)reinterpret_cast<uintptr_t>(tr.prims), src);
-                    f4 r1 = store.ld4(0), r2 = store.ld4(1);
-                    r1.x = devlib_shfl_f32(group, r1.x, src), r1.y = devlib_shfl_f32(group, r1.y, src), r1.z = devlib_shfl_f32(group, r1.z, src), r1.w = devlib_shfl_f32(group, r1.w, src);
-                    r2.x = devlib_shfl_f32(group, r2.x, src), r2.y = devlib_shfl_f32(group, r2.y, src), r2.z = devlib_shfl_f32(group, r2.z, src), r2.w = devlib_shfl_f32(group, r2.w, src);
-                    const uint32_t b_sz = __shfl_sync(group, store.ldw(CW_SZ), src), b_kz = __shfl_sync(group, store.ldw(CW_KZ), src), b_rec = __shfl_sync(group, store.ldw(CW_REC), src);
-                    if (taker && in_tlas == 0u) {
-                        tr.ox = b_ox, tr.oy = b_oy, tr.oz = b_oz, tr.idx = b_ix, tr.idy = b_iy, tr.idz = b_iz, tr.octinv = b_oct;
-                        tr.cur_inst = b_inst, tr.cur_flags = b_flags;
-                        tr.nodes = reinterpret_cast<const u4 *>(static_cast<uintptr_t>(b_nodes)), tr.prims = reinterpret_cast<const char *>(static_cast<uintptr_t>(b_prims));
-                        tr.blas_sp = 0;
-                        store.st4(0, r1), store.st4(1, r2), store.stw(CW_SZ, b_sz), store.stw(CW_KZ, b_kz), store.stw(CW_REC, b_rec);
-                    }
-                }
-            }
-        }
-        if (task) tr.step();
-    }
-    *out = best;
-}
-}// namespace lcrt
-
 [[nodiscard]] __device__ inline LCTriangleHit lc_accel_trace_closest(LCAccel accel, LCRay ray, lc_uint mask) noexcept {
-#if LCRT_TRACE_SHARED
-    lcrt::SharedBest best;
-    bool overflowed;
-    lcrt::trace_shared<lcrt::MODE_CLOSEST>(lcrt::devlib_tlas(accel), reinterpret_cast<const lcrt::Instance *>(accel.instances),
-                                           reinterpret_cast<const lcrt::Ray *>(&ray), mask, &best, &overflowed);
-    lcrt::devlib_report(accel, overflowed);
-    LCTriangleHit hit;
-    hit.m0 = best.hit ? best.inst : ~0u, hit.m1 = best.prim, hit.m2 = lc_make_float2(best.u, best.v), hit.m3 = best.hit ? (float)best.td : ray.m3;
-    return hit;// miss <=> m0 == ~0u (include/luisa/dsl/rtx/hit.h:67)
-#else
     lcrt::LocalStore store;
     lcrt::NoCallbacks cb;
     lcrt::Traversal<lcrt::MODE_CLOSEST, false, lcrt::LocalStore, lcrt::NoCallbacks> tr;
@@ -376,18 +204,9 @@ __device__ __noinline__ void trace_shared(const BlobHeader *tlas, const Instance
     lc_uint type;
     tr.result(hit.m0, hit.m1, type, hit.m3, hit.m2.x, hit.m2.y);
     return hit;// miss <=> m0 == ~0u (include/luisa/dsl/rtx/hit.h:67)
-#endif
 }
 
 [[nodiscard]] __device__ inline bool lc_accel_trace_any(LCAccel accel, LCRay ray, lc_uint mask) noexcept {
-#if LCRT_TRACE_SHARED
-    lcrt::SharedBest best;
-    bool overflowed;
-    lcrt::trace_shared<lcrt::MODE_ANY>(lcrt::devlib_tlas(accel), reinterpret_cast<const lcrt::Instance *>(accel.instances),
-                                       reinterpret_cast<const lcrt::Ray *>(&ray), mask, &best, &overflowed);
-    lcrt::devlib_report(accel, overflowed);
-    return best.hit;
-#else
     lcrt::LocalStore store;
     lcrt::NoCallbacks cb;
     lcrt::Traversal<lcrt::MODE_ANY, false, lcrt::LocalStore, lcrt::NoCallbacks> tr;
@@ -395,7 +214,6 @@ __device__ __noinline__ void trace_shared(const BlobHeader *tlas, const Instance
     tr.run();
     lcrt::devlib_report(accel, tr.overflowed());
     return tr.has_hit();
-#endif
 }
 
 // motion blur is outside this backend's scope: static scenes ignore `time`

@@ -774,9 +774,18 @@ __device__ __forceinline__ TraceSmem *trace_smem() {
     extern __shared__ __align__(16) unsigned char lcrt_trace_smem[];
     return reinterpret_cast<TraceSmem *>(lcrt_trace_smem);
 }
+// FUSED kernels: batches (128 consecutive rays reserved by one warp) whose finished records are collected before they are
+// stored to the destination: a record stored on its own is a 24-byte write, and eight GPUs sending those into one use a
+// quarter of its NVLink ingress (profiles/r2_scaling.md).  The records wait in the caller's local scratch array (L2), not in
+// shared memory: 3 KB per slot and warp there would leave the SM without L1 for the hierarchy (measured: 3.72 -> 5.51 ms per
+// C2 step at two GPUs); only the bookkeeping is per warp, in registers.
+#ifndef LCRT_STAGE_SLOTS
+#define LCRT_STAGE_SLOTS 2
+#endif
+constexpr uint32_t STAGE_SLOTS = LCRT_STAGE_SLOTS;
+
 struct HybridStore {
     static constexpr bool world_in_global = true;
-    static constexpr bool shareable = false;
     u2 local[LCRT_STACK_SIZE - TRACE_SMEM_STACK];
     __device__ __forceinline__ void store(int i, u2 v) {
         if (i < TRACE_SMEM_STACK) trace_smem()->stack[i * TRACE_BLOCK + threadIdx.x] = v;
@@ -817,16 +826,17 @@ struct TraceParams {
     int terminate_on_first;
     uint32_t magic;              // PLANT_MAGIC, see plant_byte()
     HitDest dest;                // FUSED kernels: where the final records go
+    int stage;                   // FUSED kernels: collect the records of a batch before storing them (else every record on its own)
 };
 
 // Persistent threads: every warp reserves TRACE_BATCH consecutive rays per atomic and hands them to its idle lanes
 // (ballot + popc rank) whenever at least LCRT_REFILL_MIN lanes are idle; between refills every lane advances its
 // ray by one step() per iteration.  Surface hits are written in a provisional form (u = TLAS record index, prim =
 // primitive record index, t = fp32 distance) that k_refine_hits turns into the final record.
-// FUSED (closest-hit only): the retiring lanes evaluate the exact record themselves and store it where HitDest says — a
-// framebuffer that may live in a peer GPU's memory.  The stores then leave over NVLink while the kernel is still tracing, spread
-// over its whole duration, instead of in one burst from a second pass (eight ranks storing into one at the same moment would
-// queue at its NVLink ingress).
+// FUSED (closest-hit only): the retiring lanes evaluate the exact record themselves; the records of a 128-ray batch are collected
+// (in p.out, the local scratch array) and stored where HitDest says when the batch is complete — a framebuffer that may live in a peer GPU's memory.
+// The stores then leave over NVLink while the kernel is still tracing, spread over its whole duration (not in one burst from a
+// second pass: eight ranks storing into one at the same moment queue at its NVLink ingress), in 512-byte warp stores.
 template<int MODE, bool COUNT, class Callbacks, bool FUSED = false>
 __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(TraceParams p) {
     HybridStore store;
@@ -850,21 +860,64 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
     uint64_t warp_next = 0, warp_end = 0;// this warp's reserved range of ray indices
     unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0, c_exact = 0;
     bool exhausted = false;
+    // FUSED: the batches whose records are being staged (warp-uniform): first ray, rays in the batch, rays still missing
+    uint64_t slot_base[STAGE_SLOTS] = {};
+    uint32_t slot_count[STAGE_SLOTS] = {}, slot_left[STAGE_SLOTS] = {};
     for (;;) {
         // ---- warp-cooperative retire + refill of idle lanes
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle && ((!exhausted && (uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN) || idle == 0xffffffffu)) {
+            if constexpr (MODE == MODE_CLOSEST && FUSED) {
+                // finished records go to the staging slot of their batch; a batch without a slot (both were busy when it was
+                // reserved) is stored record by record
+                uint64_t ray_idx = ~0ull;
+                uint2 r0 = make_uint2(0u, 0u), r1 = r0, r2 = r0;
+                if (unsaved) {
+                    ray_idx = (uint64_t)(tr.world - p.rays);
+                    uint32_t prim = ~0u;
+                    float t = tr.hit_t(), u = 0.f, v = 0.f;
+                    if (tr.has_hit()) refine_surface_hit(tr.world, tlas_recs, tr.hit_rec(), tr.hit_pi(), prim, t, u, v);
+                    r0 = make_uint2(tr.hit_inst(), prim), r1 = make_uint2(as_uint(u), as_uint(v)), r2 = make_uint2(as_uint(t), 0u);
+                }
+                bool staged = false;
+#pragma unroll
+                for (uint32_t sl = 0; sl < STAGE_SLOTS; sl++) {
+                    const bool mine = unsaved && slot_left[sl] != 0u && ray_idx >= slot_base[sl] && ray_idx < slot_base[sl] + slot_count[sl];
+                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                    if (m == 0u) continue;
+                    uint2 *st = reinterpret_cast<uint2 *>(static_cast<char *>(p.out) + slot_base[sl] * 24u);
+                    if (mine) {
+                        uint2 *e = st + (uint32_t)(ray_idx - slot_base[sl]) * 3u;
+                        e[0] = r0, e[1] = r1, e[2] = r2;
+                        staged = true;
+                    }
+                    slot_left[sl] -= (uint32_t)__popc(m);
+                    if (slot_left[sl] == 0u) {
+                        // the batch is complete: its records are consecutive in the destination (a batch never straddles a tile)
+                        __syncwarp();
+                        char *dst = reinterpret_cast<char *>(p.dest.at(p.out, slot_base[sl]));
+                        const uint32_t bytes = slot_count[sl] * 24u;
+                        if (dst != reinterpret_cast<char *>(st)) {
+                            if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(st) | bytes) & 15u) == 0u) {
+                                const uint4 *src = reinterpret_cast<const uint4 *>(st);
+                                for (uint32_t k = lane; k < bytes / 16u; k += 32u) __stcs(reinterpret_cast<uint4 *>(dst) + k, __ldcg(src + k));
+                            } else {
+                                for (uint32_t k = lane; k < bytes / 8u; k += 32u) __stcs(reinterpret_cast<uint2 *>(dst) + k, __ldcg(st + k));
+                            }
+                        }
+                    }
+                }
+                if (unsaved && !staged) {
+                    uint2 *o = reinterpret_cast<uint2 *>(p.dest.at(p.out, ray_idx));
+                    __stcs(o, r0), __stcs(o + 1, r1), __stcs(o + 2, r2);
+                }
+                unsaved = false;
+            }
             if (unsaved) {
                 // results are written here, together by all lanes that finished since the last refill
                 const uint64_t ray_idx = (uint64_t)(tr.world - p.rays);
                 const bool hit = tr.has_hit();
-                if constexpr (MODE == MODE_CLOSEST && FUSED) {
-                    uint32_t prim = ~0u;
-                    float t = tr.hit_t(), u = 0.f, v = 0.f;
-                    if (hit) refine_surface_hit(tr.world, tlas_recs, tr.hit_rec(), tr.hit_pi(), prim, t, u, v);
-                    uint2 *o = reinterpret_cast<uint2 *>(p.dest.at(p.out, ray_idx));
-                    __stcs(o, make_uint2(tr.hit_inst(), prim)), __stcs(o + 1, make_uint2(as_uint(u), as_uint(v))), __stcs(o + 2, make_uint2(as_uint(t), 0u));
-                } else if constexpr (MODE == MODE_CLOSEST) {
+                if constexpr (MODE == MODE_CLOSEST) {
                     u2 *o = reinterpret_cast<u2 *>(static_cast<SurfaceHit *>(p.out) + ray_idx);
 #if LCRT_STREAM_HITS
                     __stcs(reinterpret_cast<uint2 *>(o), make_uint2(tr.hit_inst(), hit ? tr.hit_pi() : ~0u));
@@ -892,6 +945,16 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                 base = __shfl_sync(0xffffffffu, base, 0);
                 warp_next = base < p.n ? base : p.n;
                 warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
+                if constexpr (MODE == MODE_CLOSEST && FUSED) {
+                    if (warp_next != warp_end && p.stage) {
+#pragma unroll
+                        for (uint32_t sl = 0; sl < STAGE_SLOTS; sl++)
+                            if (slot_left[sl] == 0u) {
+                                slot_base[sl] = warp_next, slot_count[sl] = slot_left[sl] = (uint32_t)(warp_end - warp_next);
+                                break;
+                            }
+                    }
+                }
 #if LCRT_PREFETCH_RAYS
                 // the reserved rays (TRACE_BATCH x 32 B = one 128-byte line per lane) stream from HBM exactly once
                 if (warp_next + lane * 4u < warp_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.rays + warp_next + lane * 4u));
@@ -1141,9 +1204,9 @@ static int refit_generic(cudaStream_t stream, const Input &in, void *temp, uint6
 template<int MODE, class Callbacks>
 static int trace_generic(cudaStream_t stream, const void *tlas, const void *instances, const void *rays, uint64_t n, const uint32_t *masks,
                          uint32_t mask, void *out, uint64_t *counters, uint32_t tri_prog, uint32_t proc_prog, int terminate_on_first,
-                         HitDest dest = HitDest{nullptr, 1u, 0u}) {
+                         HitDest dest = HitDest{nullptr, 1u, 0u}, bool stage = true) {
     if (n == 0) return LCRT_SUCCESS;
-    if (dest.dst != nullptr && (MODE == MODE_ANY || dest.tile == 0u || (reinterpret_cast<uintptr_t>(dest.dst) & 7u) || (dest.stride & 7u) ||
+    if (dest.dst != nullptr && (MODE == MODE_ANY || dest.tile == 0u || dest.tile % TRACE_BATCH != 0u || (reinterpret_cast<uintptr_t>(dest.dst) & 7u) || (dest.stride & 7u) ||
                                 dest.stride < dest.tile * 24u))
         return LCRT_ERROR_INVALID_VALUE;
     if (tlas == nullptr || rays == nullptr || out == nullptr) return LCRT_ERROR_INVALID_VALUE;
@@ -1162,21 +1225,24 @@ static int trace_generic(cudaStream_t stream, const void *tlas, const void *inst
     static const bool force_fused = getenv("LCRT_FUSED_REFINE") != nullptr && atoi(getenv("LCRT_FUSED_REFINE")) != 0;
     const bool fused = MODE == MODE_CLOSEST && counters == nullptr && (dest.dst != nullptr || force_fused);
     p.dest = dest;
-    auto launch = [&](auto kernel) -> int {
+    p.stage = stage ? 1 : 0;
+    auto launch = [&](auto kernel, size_t smem) -> int {
         int bps = 0;
-        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, TRACE_BLOCK, sizeof(TraceSmem)));
+        LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, TRACE_BLOCK, smem));
         if (bps < 1) bps = 1;
+        static const bool verbose = getenv("LCRT_VERBOSE") != nullptr;
+        if (verbose) fprintf(stderr, "[lcrt] k_trace mode %d: %zu B shared memory per block, %d blocks per SM\n", MODE, smem, bps);
         uint64_t g = (uint64_t)dev->sm_count * (uint64_t)bps;
         const uint64_t need = (n + TRACE_BLOCK - 1) / TRACE_BLOCK;
         if (g > need) g = need;
-        kernel<<<(uint32_t)g, TRACE_BLOCK, sizeof(TraceSmem), stream>>>(p);
+        kernel<<<(uint32_t)g, TRACE_BLOCK, smem, stream>>>(p);
         LCRT_LAUNCH_CHECK("k_trace");
         return LCRT_SUCCESS;
     };
     int rc;
-    if (counters) rc = launch(k_trace<MODE, true, Callbacks, false>);
-    else if (fused) rc = launch(k_trace<MODE, false, Callbacks, MODE == MODE_CLOSEST>);
-    else rc = launch(k_trace<MODE, false, Callbacks, false>);
+    if (counters) rc = launch(k_trace<MODE, true, Callbacks, false>, sizeof(TraceSmem));
+    else if (fused) rc = launch(k_trace<MODE, false, Callbacks, MODE == MODE_CLOSEST>, sizeof(TraceSmem));
+    else rc = launch(k_trace<MODE, false, Callbacks, false>, sizeof(TraceSmem));
     if (rc != LCRT_SUCCESS) return rc;
     if (MODE != MODE_ANY && !fused) {
         k_refine_hits<MODE><<<(uint32_t)((n + 255u) / 256u), 256, 0, stream>>>(p.tlas, p.rays, out, n, dest);
@@ -1307,10 +1373,12 @@ int lcrtTraceClosest(lcrtStream stream, const void *tlas, const void *instances,
 }
 
 int lcrtTraceClosestTiled(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,
-                          uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays, uint64_t tile_stride_bytes, uint64_t *counters) {
+                          uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays, uint64_t tile_stride_bytes, uint32_t flags,
+                          uint64_t *counters) {
     if (dst == nullptr) return LCRT_ERROR_INVALID_VALUE;
     return trace_generic<MODE_CLOSEST, NoCallbacks>(static_cast<cudaStream_t>(stream), tlas, instances, rays, ray_count, masks, mask, scratch_hits,
-                                                    counters, 0, 0, 0, HitDest{static_cast<char *>(dst), tile_rays, tile_stride_bytes});
+                                                    counters, 0, 0, 0, HitDest{static_cast<char *>(dst), tile_rays, tile_stride_bytes},
+                                                    (flags & LCRT_TILED_STORE_EACH_RECORD) == 0u);
 }
 
 int lcrtTraceAny(lcrtStream stream, const void *tlas, const void *instances, const void *rays, uint64_t ray_count, const uint32_t *masks,

@@ -86,7 +86,6 @@ enum ColdWord : int {
 };
 struct LocalStore {
     static constexpr bool world_in_global = false;
-    static constexpr bool shareable = false;// Traversal::bottom is always 0
     u2 e[LCRT_STACK_SIZE];
     f4 rows[2];
     uint32_t words[CW_COUNT];
@@ -357,12 +356,6 @@ LCRT_HD bool refine_surface_hit(const Ray *world, const InstanceRecord *tlas_rec
     return true;
 }
 
-// LocalStore of a traversal whose oldest stack entries can be handed to other lanes of the warp (lcrt_device_library.cuh,
-// trace_shared): the stack then has a moving bottom
-struct SharedLocalStore : LocalStore {
-    static constexpr bool shareable = true;
-};
-
 // --------------------------------------------------------------------------------------------------------------
 // Traversal state machine.  `step()` performs one outer iteration (at most one node, then at most one primitive);
 // the persistent batch kernel interleaves step() with warp-cooperative ray refetch, the inline device-library
@@ -381,7 +374,6 @@ struct Traversal {
     u2 Gt;             // primitive group: x = node index, y = pending leaf slots | remaining prims of the current slot << 8
     uint32_t tp;       // next primitive record of the current slot
     int sp, blas_sp;   // blas_sp < 0: traversing the TLAS
-    int bottom = 0;    // first stack entry that is still this traversal's (entries below were given away; shareable stores only)
     uint32_t cur_inst, cur_flags, ray_mask;
     bool done;
     // ---- level-independent
@@ -450,7 +442,7 @@ struct Traversal {
         G = single ? make_u2(0u, 0u) : make_u2(0u, 0x80000000u);
         Gt = single ? make_u2(0u, 1u << 8) : make_u2(0u, 0u);
         tp = 0u;
-        sp = 0, blas_sp = -1, bottom = 0;
+        sp = 0, blas_sp = -1;
         cur_inst = ~0u, cur_flags = 0u;
         store->stw(CW_HIT_T, as_uint(tmax_)), store->stw(CW_HIT_TERR, as_uint(-1.0f));
         store->stw(CW_HIT_INST, ~0u), store->stw(CW_HIT_PRIM, ~0u), store->stw(CW_HIT_TYPE, HIT_MISS);
@@ -683,10 +675,6 @@ struct Traversal {
         if (done) return false;
         // ---- pop when both groups are exhausted
         if ((G.y & 0xff000000u) == 0u && Gt.y == 0u) {
-            if (Store::shareable && sp == bottom) {// (before the level check: with the TLAS entries given away, the instance is the end)
-                done = true;
-                return false;
-            }
             if (blas_sp >= 0 && sp == blas_sp) leave_instance();
             if (sp == 0) {
                 done = true;

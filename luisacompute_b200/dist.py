@@ -191,15 +191,49 @@ class PeerFramebuffer:
         # the owner's view of the whole buffer, ray order
         self.full = torch.as_tensor(_RawCudaBuffer(self.address, self.bytes // 4), device=tdev).view(-1, words) if self.owner else None
 
-    def trace_closest(self, accel, rays, mask=0xFF, scratch=None, first_local_tile: int = 0):
-        """Traces this rank's rays (local tiles first_local_tile ...) and stores the records into the framebuffer."""
-        return accel.trace_closest_tiled(rays, self.base + first_local_tile * self.stride, self.tile, self.stride, mask=mask, scratch=scratch)
+    def trace_closest(self, accel, rays, mask=0xFF, scratch=None, first_local_tile: int = 0, store_each_record=None):
+        """Traces this rank's rays (local tiles first_local_tile ...) and stores the records into the framebuffer FROM THE TRACE
+        KERNEL: no second pass, no copy, the stores leave over NVLink while the kernel is still tracing.  By default the
+        records of a 128-ray batch go out together when the batch is complete (512-byte warp stores) when more than two
+        ranks write into the owner, and one by one as the rays end otherwise: single 24-byte stores cost the kernel less, but
+        eight GPUs sending them into one use its NVLink ingress badly (profiles/r2_scaling.md)."""
+        if store_each_record is None:
+            store_each_record = self.world <= 2
+        return accel.trace_closest_tiled(rays, self.base + first_local_tile * self.stride, self.tile, self.stride, mask=mask, scratch=scratch,
+                                         store_each_record=store_each_record)
+
+    def submit(self, hits, first_local_tile: int, after=None):
+        """Queues the copy of finished local tiles (`hits`: int32 [k * tile, words], contiguous, final records) to where ray
+        order puts them in the framebuffer: ONE strided device-to-device copy on a side stream, executed by the copy engines
+        over NVLink, behind the CUDA event `after` (recorded when the chunk's trace was enqueued) — it runs while the SMs
+        trace the next chunk."""
+        import torch
+
+        from . import _check, lib
+        k = hits.shape[0] // self.tile
+        assert hits.is_contiguous() and hits.shape[0] == k * self.tile
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(self.device.torch_device, priority=-1)
+        if after is not None:
+            self._copy_stream.wait_event(after)
+        else:
+            self._copy_stream.wait_stream(torch.cuda.current_stream(self.device.torch_device))
+        _check(lib().lcbFramebufferCopyTiles(self.device._h, self._copy_stream.cuda_stream, hits.data_ptr(), self.base + first_local_tile * self.stride,
+                                             self.tile_bytes, self.stride, k), "lcbFramebufferCopyTiles")
+
+    def complete_local(self):
+        """The caller's stream waits for this framebuffer's queued copies (no collective)."""
+        import torch
+        if hasattr(self, "_copy_stream"):
+            torch.cuda.current_stream(self.device.torch_device).wait_stream(self._copy_stream)
 
     def complete(self):
-        """Every rank's stores of the step are in the owner's memory once this returns on the owner's stream: kernel completion
-        makes them visible system-wide, the (tiny) all-reduce orders the owner's stream behind every rank's kernels."""
+        """Every rank's records of the step are in the owner's memory once this returns on the owner's stream: kernel / copy
+        completion makes them visible system-wide, the (tiny) all-reduce orders the owner's stream behind every rank's work."""
         import torch
         import torch.distributed as dist
+        if hasattr(self, "_copy_stream"):
+            torch.cuda.current_stream(self.device.torch_device).wait_stream(self._copy_stream)
         if self.world > 1:
             if not hasattr(self, "_token"):
                 self._token = torch.zeros(1, dtype=torch.int32, device=self.device.torch_device)

@@ -637,14 +637,15 @@ int lcbTraceClosest(lcbDevice *device, lcrtStream stream, uint64_t accel, const 
 }
 
 int lcbTraceClosestTiled(lcbDevice *device, lcrtStream stream, uint64_t accel, const void *rays, uint64_t ray_count, const uint32_t *masks,
-                         uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays, uint64_t tile_stride_bytes, uint64_t *counters) {
+                         uint32_t mask, void *scratch_hits, void *dst, uint64_t tile_rays, uint64_t tile_stride_bytes, uint32_t flags,
+                         uint64_t *counters) {
     LCB_DEVICE_GUARD(device);
     auto a = device->find<lcb::Accel>(accel, lcb::Resource::Tag::ACCEL);
     if (!a || !a->built) return LCRT_ERROR_INVALID_VALUE;
     device->note_stream(static_cast<cudaStream_t>(stream));
     a->check_pending = true;
     return lcrtTraceClosestTiled(stream, a->blob, a->instance_buffer, rays, ray_count, masks, mask, scratch_hits, dst, tile_rays, tile_stride_bytes,
-                                 counters);
+                                 flags, counters);
 }
 
 // ---- framebuffers shared between the processes of a node (one process per GPU): CUDA IPC over plain cudaMalloc memory
@@ -679,6 +680,16 @@ int lcbFramebufferOpen(lcbDevice *device, const unsigned char handle[64], uint64
 int lcbFramebufferClose(lcbDevice *device, uint64_t address) {
     LCB_DEVICE_GUARD(device);
     LCB_CUDA(cudaIpcCloseMemHandle(reinterpret_cast<void *>(address)));
+    return LCRT_SUCCESS;
+}
+
+int lcbFramebufferCopyTiles(lcbDevice *device, lcrtStream stream, const void *src, uint64_t dst, uint64_t tile_bytes, uint64_t dst_stride_bytes,
+                            uint64_t tile_count) {
+    LCB_DEVICE_GUARD(device);
+    if (tile_count == 0) return LCRT_SUCCESS;
+    if (!src || !dst || tile_bytes == 0 || dst_stride_bytes < tile_bytes) return LCRT_ERROR_INVALID_VALUE;
+    LCB_CUDA(cudaMemcpy2DAsync(reinterpret_cast<void *>(dst), dst_stride_bytes, src, tile_bytes, tile_bytes, tile_count, cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(stream)));
     return LCRT_SUCCESS;
 }
 

@@ -27,12 +27,41 @@ def test_framebuffer_single_rank_equals_in_place(scene):
     dev, acc, rays = scene
     ref = acc.trace_closest(rays)
     fb = PeerFramebuffer(dev, n_local_tiles=8, tile=16384)
+    for each in (False, True):      # records of a 128-ray batch stored together / every record on its own
+        fb.full.fill_(0x55555555)
+        fb.trace_closest(acc, rays, store_each_record=each)
+        fb.complete()
+        torch.cuda.synchronize()
+        assert torch.equal(fb.full, ref), each
+    assert int((ref[:, 0] == -1).sum()) > 1000 and int((ref[:, 0] != -1).sum()) > 1000   # misses and hits both went through
+    fb.close()
+
+
+def test_copy_engine_path_fills_ray_order(scene):
+    """PeerFramebuffer.submit: finished local tiles go to their ray-order places with one strided copy per chunk."""
+    import torch
+    from luisacompute_b200.dist import PeerFramebuffer
+    dev, acc, rays = scene
+    ref = acc.trace_closest(rays)
+    fb = PeerFramebuffer(dev, n_local_tiles=8, tile=16384)
     fb.full.fill_(0x55555555)
-    fb.trace_closest(acc, rays)
+    for t0 in range(0, 8, 3):                       # ragged chunks: 3 + 3 + 2 tiles
+        t1 = min(t0 + 3, 8)
+        ev = torch.cuda.Event()
+        ev.record()
+        fb.submit(ref[t0 * 16384:t1 * 16384], t0, ev)
     fb.complete()
     torch.cuda.synchronize()
     assert torch.equal(fb.full, ref)
-    assert int((ref[:, 0] == -1).sum()) > 1000 and int((ref[:, 0] != -1).sum()) > 1000   # misses and hits both went through
+    # with a stride: the tiles of "rank 1 of 2" interleave with untouched ones
+    fb.full.fill_(7)
+    fb.world, fb.stride, fb.base = 2, 2 * fb.tile_bytes, fb.address + fb.tile_bytes
+    fb.submit(ref[:4 * 16384], 0)
+    torch.cuda.current_stream().wait_stream(fb._copy_stream)
+    torch.cuda.synchronize()
+    v = fb.full.view(4, 2, 16384, 6)
+    assert torch.equal(v[:, 1].reshape(-1, 6), ref[:4 * 16384]) and bool((v[:, 0] == 7).all())
+    fb.world = 1
     fb.close()
 
 

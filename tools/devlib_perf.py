@@ -1,5 +1,5 @@
 """Developer tool (GPU box): the inline entry points lc_accel_trace_closest / _any (what generated kernels call, one thread per
-ray) on the C2 workload, with and without work sharing between the lanes of a warp, next to the batch kernel.
+ray) on the C2 workload next to the batch kernel; developer variants of the test kernels in gpurun_variants/ are timed too.
 usage: python tools/devlib_perf.py [--level 8] [--res 2048] [--block 128]"""
 import argparse
 import ctypes as C
@@ -32,7 +32,7 @@ def timeit(fn, reps=5, warm=2):
 
 
 def load(name):
-    L = C.CDLL(os.path.join(ROOT, "tests", "devlib", name))
+    L = C.CDLL(name if os.path.isabs(name) else os.path.join(ROOT, "tests", "devlib", name))
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     L.dl_closest.argtypes = [vp, u64, vp, vp, u32, u32, vp, u32]
     L.dl_any.argtypes = [vp, u64, vp, vp, u32, u32, vp, u32]
@@ -68,7 +68,11 @@ def main():
                                     "incoherent_any": n / timeit(lambda: acc.trace_any(d_b, out=ref_any)) / 1e3}}
     hits = torch.empty((n, 6), dtype=torch.int32, device="cuda")
     occ = torch.empty(n, dtype=torch.int32, device="cuda")
-    for name, so in (("shared", "libdevlibtest.so"), ("one_lane_one_ray", "libdevlibtest_noshare.so")):
+    libs = [("inline_entry_points", "libdevlibtest.so")]
+    vdir = os.path.join(ROOT, "gpurun_variants")   # developer variants (tools/_build_devlib_variants.sh)
+    if os.path.isdir(vdir):
+        libs += [(f[len("libdevlibtest_"):-3], os.path.join(vdir, f)) for f in sorted(os.listdir(vdir)) if f.startswith("libdevlibtest_")]
+    for name, so in libs:
         L = load(so)
         r = {}
         for label, rays, ref in (("coherent", d_p, ref_p), ("incoherent", d_b, ref_b)):
