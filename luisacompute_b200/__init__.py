@@ -190,10 +190,19 @@ def lib():
     return L
 
 
+_DEBUG_SYNC = os.environ.get("LCB200_DEBUG_SYNC") == "1"   # developer aid: name every call, then wait for the device
+
+
 def _check(rc: int, what: str) -> None:
     if rc != 0:
         L = lib()
         raise LcrtError(f"{what} failed: {L.lcrtGetErrorString(rc).decode()} [{L.lcrtGetLastCudaError().decode()}]")
+    if _DEBUG_SYNC:
+        import sys
+        import torch
+        print(f"[lcb200] {what} ...", end="", file=sys.stderr, flush=True)
+        torch.cuda.synchronize()
+        print(" done", file=sys.stderr, flush=True)
 
 
 def _stream() -> int:

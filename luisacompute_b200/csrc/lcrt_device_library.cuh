@@ -407,3 +407,66 @@ void lc_ray_query_trace(LCRayQuery &q, lc_uint impl_tag, void *ctx) noexcept {
     tr.result(q.hit.m0, q.hit.m1, q.hit.m3, q.hit.m4, q.hit.m2.x, q.hit.m2.y);
     if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
 }
+
+// ------------------------------------------------------------------------------------------ RayQuery, lowered inline
+// What the inline lowering of RayQueryStmt calls (plugin/hybrid/b200_ray_query_lowering.inl emits it when the codegen is told
+// to; SURVEY.md 7.7, the shape of src/backends/common/hlsl/hlsl_codegen.cpp:555-567):
+//
+//     { LCRayQueryInline lc_rq;
+//       lc_ray_query_inline_begin(lc_rq, q);
+//       while (lc_ray_query_inline_proceed(lc_rq)) {
+//           LCIntersectionResult result{};
+//           const LCRTCandidate &lc_rt_candidate = lc_rq.candidate;
+//           if (lc_rq.triangle_candidate) { ...on_triangle_candidate body... } else { ...on_procedural_candidate body... }
+//           lc_ray_query_inline_resolve(lc_rq, result);
+//       }
+//       lc_ray_query_inline_end(lc_rq, q); }
+//
+// The handler bodies are the statements the outlined form puts into LUISA_DECL_RAY_QUERY_*_IMPL functions, with the same
+// LC_RAY_QUERY_* macros — but in the kernel's own scope: what they read and write are the kernel's variables, not copies in a
+// capture struct behind a `void *` (cuda_codegen_ast.cpp:446-521, 562-617).  The traversal is suspended at every candidate
+// (SuspendingCallbacks) and resumed by the next proceed.  With one RayQuery site per kernel proceed is inlined and the
+// traversal state stays in registers across the handler; with several, ONE out-of-line copy serves them all (the instruction-
+// cache lesson of profiles/r1_c5_ncu.md) and the state crosses the call in local memory.
+struct LCRayQueryInline {
+    lcrt::LocalStore store;
+    lcrt::SuspendingCallbacks cb;
+    lcrt::Traversal<lcrt::MODE_QUERY, false, lcrt::LocalStore, lcrt::SuspendingCallbacks> tr;
+    LCRTCandidate candidate;
+    lc_bool triangle_candidate;
+};
+#ifndef LCRT_RAY_QUERY_SITE_COUNT
+#define LCRT_RAY_QUERY_SITE_COUNT 1
+#endif
+__device__ inline void lc_ray_query_inline_begin(LCRayQueryInline &s, LCRayQuery &q) noexcept {
+    s.cb.pend.kind = 0;
+    s.tr.init(lcrt::devlib_tlas(q.accel), reinterpret_cast<const lcrt::Instance *>(q.accel.instances), reinterpret_cast<const lcrt::Ray *>(&q.ray), q.mask,
+              &s.store, &s.cb);
+    s.tr.terminate_on_first = (q.flags & LC_RAY_FLAG_TERMINATE_ON_FIRST_HIT) != 0u;
+}
+#if LCRT_RAY_QUERY_SITE_COUNT <= 1
+[[nodiscard]] __device__ inline
+#else
+[[nodiscard]] __device__ __noinline__
+#endif
+bool lc_ray_query_inline_proceed(LCRayQueryInline &s) noexcept {
+    while (s.tr.step()) {
+        if (!s.tr.candidate_pending()) continue;
+        const lcrt::PendingCandidate &pc = s.cb.pend;
+        s.triangle_candidate = pc.kind == 1;
+        s.candidate = LCRTCandidate{};
+        if (pc.kind == 1) s.candidate.triangle = LCTriangleHit{pc.inst, pc.prim, lc_make_float2(pc.u, pc.v), pc.t};
+        else s.candidate.procedural = LCProceduralHit{pc.inst, pc.prim};
+        s.candidate.world_ray = lcrt::DevlibQueryCallbacks::to_lc_ray(s.tr.candidate_ray());
+        return true;
+    }
+    return false;
+}
+__device__ inline void lc_ray_query_inline_resolve(LCRayQueryInline &s, const LCIntersectionResult &r) noexcept {
+    s.tr.resolve(r.committed, r.terminated, r.t_hit);
+}
+__device__ inline void lc_ray_query_inline_end(LCRayQueryInline &s, LCRayQuery &q) noexcept {
+    lcrt::devlib_report(q.accel, s.tr.overflowed());
+    s.tr.result(q.hit.m0, q.hit.m1, q.hit.m3, q.hit.m4, q.hit.m2.x, q.hit.m2.y);
+    if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
+}

@@ -748,6 +748,18 @@ constexpr uint32_t TRACE_BATCH = LCRT_TRACE_BATCH; // rays a warp reserves per a
 #ifndef LCRT_TRACE_MIN_BLOCKS
 #define LCRT_TRACE_MIN_BLOCKS 5     // resident blocks per SM the register allocation is bounded for
 #endif
+#ifndef LCRT_TRI_VOTE_PATIENCE
+#define LCRT_TRI_VOTE_PATIENCE 128
+#endif
+// The vote makes a lane with a pending primitive wait for company.  In RayQuery batches such a lane was seen to wait FOREVER
+// (BASELINE C5, the 2 Mi bounce rays of tests/test_gpu_fullsize.py::test_c5_fullsize: the launch never ended in about half of
+// the runs, never without the vote, never in the host simulation of the same schedule): RayQuery launches therefore bound the
+// wait (a warp-uniform counter: after LCRT_TRI_VOTE_PATIENCE refusals in a row the primitive phase runs regardless).
+// Closest / any-hit launches have never shown it and pay 4 % for the counter (2392 -> 2296 Mrays/s coherent on C2), so there it
+// is compiled in only with LCRT_TRI_VOTE_VALVE_ALL_MODES=1.  profiles/r2_trace_experiments.md.
+#ifndef LCRT_TRI_VOTE_VALVE_ALL_MODES
+#define LCRT_TRI_VOTE_VALVE_ALL_MODES 0
+#endif
 #ifndef LCRT_TRI_VOTE
 #define LCRT_TRI_VOTE 4               // lanes with a pending primitive that make the warp run the primitive phase
 #endif
@@ -860,6 +872,7 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
     uint64_t warp_next = 0, warp_end = 0;// this warp's reserved range of ray indices
     unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0, c_exact = 0;
     bool exhausted = false;
+    uint32_t denied = 0u;// consecutive iterations in which lanes with a pending primitive were made to wait (warp-uniform)
     // FUSED: the batches whose records are being staged (warp-uniform): first ray, rays in the batch, rays still missing
     uint64_t slot_base[STAGE_SLOTS] = {};
     uint32_t slot_count[STAGE_SLOTS] = {}, slot_left[STAGE_SLOTS] = {};
@@ -971,6 +984,19 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
             }
             warp_next += want < avail ? want : avail;
         }
+#ifdef LCRT_TRACE_WATCHDOG
+        // developer aid: a ray that is still being traversed after this many iterations is reported and dropped
+        {
+            static_assert(sizeof(unsigned long long) == 8, "");
+            if (active && ++c_nodes > (unsigned long long)LCRT_TRACE_WATCHDOG) {
+                printf("[lcrt watchdog] ray %llu block %u thread %u: sp %d blas_sp %d G (%u, %08x) Gt (%u, %08x) tp %u inst %u flags %08x octinv %08x tmin %g tmax %g done %d\n",
+                       (unsigned long long)(tr.world - p.rays), blockIdx.x, threadIdx.x, tr.sp, tr.blas_sp, tr.G.x, tr.G.y, tr.Gt.x, tr.Gt.y, tr.tp, tr.cur_inst,
+                       tr.cur_flags, tr.octinv, (double)tr.tmin, (double)tr.tmax, (int)tr.done);
+                tr.done = true;
+            }
+            if (!active) c_nodes = 0;
+        }
+#endif
         // ---- one traversal step per lane: a node, then (if the warp votes for it) a primitive
         bool alive = active && tr.step_node();
 #if LCRT_TRI_VOTE > 0
@@ -979,7 +1005,21 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
             // lanes with a pending primitive wait until LCRT_TRI_VOTE of them (or every live lane) can go together
             const uint32_t am = __ballot_sync(0xffffffffu, alive);
             const uint32_t pm = __ballot_sync(0xffffffffu, alive && tr.prim_pending());
-            if ((uint32_t)__popc(pm) >= (uint32_t)LCRT_TRI_VOTE || pm == am) alive = alive && tr.step_prim();
+            // (a lane is never made to wait more than LCRT_TRI_VOTE_PATIENCE iterations: liveness does not rest on the other
+            // lanes' traversals)
+#if LCRT_TRI_VOTE_VALVE_ALL_MODES
+            constexpr bool valve = true;
+#else
+            constexpr bool valve = MODE == MODE_QUERY;
+#endif
+            bool go = (uint32_t)__popc(pm) >= (uint32_t)LCRT_TRI_VOTE || pm == am;
+            if constexpr (valve) go = go || denied >= (uint32_t)LCRT_TRI_VOTE_PATIENCE;
+            if (go) {
+                alive = alive && tr.step_prim();
+                if constexpr (valve) denied = 0u;
+            } else if constexpr (valve) {
+                if (pm != 0u) denied++;
+            }
         }
 #else
         alive = alive && tr.step_prim();

@@ -64,6 +64,31 @@ struct NoCallbacks {
     LCRT_HD CandidateResult on_procedural(uint32_t, uint32_t, const Ray &, const Instance *, const f4, const f4) const { return {0.f, false, false}; }
 };
 
+// A RayQuery whose candidate handlers run in the CALLER's scope (the inline lowering of RayQueryStmt, SURVEY.md 7.7: `while
+// (proceed) { handler }` as in src/backends/common/hlsl/hlsl_codegen.cpp:555-567): a callbacks type that declares
+// `suspends` is never called — the traversal records the candidate in its `pend` member and returns from the step; the caller
+// runs the handler and hands the verdict back through Traversal::resolve().
+struct PendingCandidate {
+    int kind;// 0 none, 1 triangle (non-opaque instance), 2 procedural primitive
+    uint32_t inst, prim, pi;
+    float t, terr, u, v;// triangle: the candidate hit
+    float ht;           // what the handler sees as the ray's t_max: the candidate's t (triangle), the committed distance (procedural)
+    bool exact;
+    double td;
+};
+struct SuspendingCallbacks {
+    static constexpr bool suspends = true;
+    PendingCandidate pend;
+    LCRT_HD CandidateResult on_triangle(uint32_t, uint32_t, float, float, float, const Ray &) const { return {0.f, false, false}; }
+    LCRT_HD CandidateResult on_procedural(uint32_t, uint32_t, const Ray &, const Instance *, const f4, const f4) const { return {0.f, false, false}; }
+};
+template<class C>
+struct callbacks_suspend {
+    template<class T> static char test(decltype(T::suspends) *);
+    template<class T> static long test(...);
+    static constexpr bool value = sizeof(test<C>(nullptr)) == sizeof(char);
+};
+
 // Per-ray storage outside the register file: the traversal stack plus the "cold" ray state that is touched once per
 // primitive test or once per accepted hit.  The batch kernel keeps the first stack entries and all cold state in
 // shared memory (lcrt_kernels.cu HybridStore); this plain version serves the host simulation and the inline
@@ -621,6 +646,14 @@ struct Traversal {
             if (!take) return false;
             t = (float)td, terr = 1.2e-7f * fabsf(t), exact = true;
         }
+        if constexpr (callbacks_suspend<Callbacks>::value) {
+            if (candidate_program) {// the caller runs the handler (resolve())
+                PendingCandidate &pc = cb->pend;
+                pc.kind = 1, pc.inst = cur_inst, pc.prim = prim, pc.pi = pi, pc.t = t, pc.terr = terr, pc.u = u, pc.v = v, pc.ht = t;
+                pc.exact = exact, pc.td = td;
+                return false;
+            }
+        }
         if (candidate_program) {
             Ray wr = *world;
             wr.tmax = t;// accel.rs:663-672: tmax shrinks to the candidate while the callback runs
@@ -630,6 +663,33 @@ struct Traversal {
         }
         accept(t, terr, prim, pi, HIT_SURFACE, exact, td);
         return MODE == MODE_ANY || MODE_ANY_QUERY();
+    }
+
+    // ---- suspending callbacks: the candidate the last step left for the caller, and its verdict
+    LCRT_HD bool candidate_pending() const {
+        if constexpr (callbacks_suspend<Callbacks>::value) return cb->pend.kind != 0;
+        else return false;
+    }
+    LCRT_HD Ray candidate_ray() const {// the world ray as the handler sees it (accel.rs:663-672, 705-716)
+        Ray wr = *world;
+        if constexpr (callbacks_suspend<Callbacks>::value) wr.tmax = cb->pend.ht;
+        return wr;
+    }
+    LCRT_HD void resolve(bool committed, bool terminated, float t_hit) {
+        if constexpr (callbacks_suspend<Callbacks>::value) {
+            const PendingCandidate pc = cb->pend;
+            cb->pend.kind = 0;
+            if (pc.kind == 1) {
+                if (committed) accept(pc.t, pc.terr, pc.prim, pc.pi, HIT_SURFACE, pc.exact, pc.td);
+                if (terminated || (committed && MODE_ANY_QUERY())) done = true;
+            } else if (pc.kind == 2) {
+                if (committed && t_hit >= tmin && t_hit < pc.ht) {// accel.rs:711-713
+                    accept(t_hit, 0.f, pc.prim, pc.pi, HIT_PROCEDURAL, true, (double)t_hit);
+                    if (MODE_ANY_QUERY()) done = true;
+                }
+                if (terminated) done = true;
+            }
+        }
     }
 
     // step() = step_node() followed by step_prim(); the batch kernel calls the halves separately so that the warp can
@@ -746,6 +806,11 @@ struct Traversal {
                         const float ht = store->ldw(CW_HIT_INST) != ~0u ? (float)best_exact_t() : hit_t();
                         wr.tmax = ht;
                         const uint32_t prim = as_uint(lo.w);
+                        if constexpr (callbacks_suspend<Callbacks>::value) {
+                            PendingCandidate &pc = cb->pend;
+                            pc.kind = 2, pc.inst = cur_inst, pc.prim = prim, pc.pi = pi, pc.ht = ht;
+                            return true;// the caller runs the handler (resolve())
+                        }
                         const CandidateResult r = cb->on_procedural(cur_inst, prim, wr, instances, lo, hi);
                         if (r.committed && r.t_hit >= tmin && r.t_hit < ht) {// accel.rs:711-713
                             accept(r.t_hit, 0.f, prim, pi, HIT_PROCEDURAL, true, (double)r.t_hit);

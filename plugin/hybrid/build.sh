@@ -6,6 +6,8 @@
 #     this repository's device library (plugin/hybrid/make_device_resource.py), same array size
 #   * cuda_shader_optix  ->  plugin/hybrid/b200_shader_rt.cpp: kernels that trace rays are launched with cuLaunchKernel
 #   * optix_api          ->  plugin/hybrid/b200_optix_stub.cpp: libnvoptix is never opened
+#   * cuda_codegen_ast   ->  the same translation unit with class RayQueryLowering replaced by plugin/hybrid/b200_ray_query_lowering.inl
+#     (make_codegen.py splices it into a build-time copy): RayQuery handlers are emitted inline, `while (proceed) { handler }`
 # swapped in at link time.  Reference sources are neither modified nor copied.  usage: build.sh [REF] [BUILD] [OUT]
 set -e
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -25,13 +27,18 @@ objcopy --weaken-symbol=luisa_cuda_builtin_cuda_device_resource "$OBJ/cuda_built
 cmd=$(ninja -C "$BD" -t commands luisa-compute-backend-cuda | grep -E "/cuda_accel\.cpp\.o " | head -1)
 rt=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/b200_cuda_rt.o#; s# -c [^ ]*cuda_accel\.cpp# -I$REF/src/backends/cuda -I$ROOT/include -c $HERE/b200_cuda_rt.cpp#; s# -MD -MT [^ ]* -MF [^ ]*##")
 (cd "$BD" && eval "$rt")
+# the code generator with this repository's RayQuery lowering (inline `while (proceed) { handler }` loops; the reference's outlined
+# form stays available behind LUISA_B200_RAY_QUERY=outline): a build-time copy of cuda_codegen_ast.cpp, see make_codegen.py
+python "$HERE/make_codegen.py" "$REF/src/backends/cuda/cuda_codegen_ast.cpp" "$HERE/b200_ray_query_lowering.inl" "$W/b200_codegen_ast.cpp"
+cg=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/b200_codegen_ast.o#; s# -c [^ ]*cuda_accel\.cpp# -I$REF/src/backends/cuda -c $W/b200_codegen_ast.cpp#; s# -MD -MT [^ ]* -MF [^ ]*##")
+(cd "$BD" && eval "$cg")
 for unit in b200_shader_rt b200_optix_stub; do
   one=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/$unit.o#; s# -c [^ ]*cuda_accel\.cpp# -I$REF/src/backends/cuda -I$ROOT/include -c $HERE/$unit.cpp#; s# -MD -MT [^ ]* -MF [^ ]*##")
   (cd "$BD" && eval "$one")
 done
 link=$(ninja -C "$BD" -t commands luisa-compute-backend-cuda | grep -E "^: && .* -o bin/liblc-backend-cuda.so" | sed -E 's#^: && ##; s# && cd .*$##')
-link=$(echo "$link" | sed -E "s# [^ ]*/cuda_accel\.cpp\.o##; s# [^ ]*/cuda_mesh\.cpp\.o##; s# [^ ]*/cuda_primitive\.cpp\.o##; s# [^ ]*/cuda_procedural_primitive\.cpp\.o##; s# [^ ]*/cuda_builtin_embedded\.cpp\.o##; s# [^ ]*/cuda_shader_optix\.cpp\.o##; s# [^ ]*/optix_api\.cpp\.o##")
-link=${link/ -o bin\/liblc-backend-cuda.so / -o bin/liblc-backend-b200.so $OBJ/ref_cuda_vulkan_stubs.o $W/b200_cuda_rt.o $W/b200_shader_rt.o $W/b200_optix_stub.o $W/b200_device_resource.o $W/cuda_builtin_embedded_weak.o }
+link=$(echo "$link" | sed -E "s# [^ ]*/cuda_accel\.cpp\.o##; s# [^ ]*/cuda_mesh\.cpp\.o##; s# [^ ]*/cuda_primitive\.cpp\.o##; s# [^ ]*/cuda_procedural_primitive\.cpp\.o##; s# [^ ]*/cuda_builtin_embedded\.cpp\.o##; s# [^ ]*/cuda_shader_optix\.cpp\.o##; s# [^ ]*/optix_api\.cpp\.o##; s# [^ ]*/cuda_codegen_ast\.cpp\.o##")
+link=${link/ -o bin\/liblc-backend-cuda.so / -o bin/liblc-backend-b200.so $OBJ/ref_cuda_vulkan_stubs.o $W/b200_cuda_rt.o $W/b200_shader_rt.o $W/b200_optix_stub.o $W/b200_codegen_ast.o $W/b200_device_resource.o $W/cuda_builtin_embedded_weak.o }
 cp -f "$ROOT/luisacompute_b200/liblcb200_rt.so" "$BD/bin/"
 (cd "$BD" && eval "$link -L$BD/bin -llcb200_rt")
 cp -f "$BD/bin/liblc-backend-b200.so" "$ROOT/luisacompute_b200/liblcb200_rt.so" "$OUT"/

@@ -11,6 +11,7 @@
 
 #define LCRT_DEVLIB_STANDALONE
 #define LUISA_RAY_QUERY_IMPL_COUNT 2
+#define LCRT_RAY_QUERY_SITE_COUNT 2
 #include "../../luisacompute_b200/csrc/lcrt_device_library.cuh"
 
 // ---- what `Kernel1D` argument structs look like after the codegen (resources passed by value)
@@ -132,6 +133,77 @@ extern "C" __global__ void k_devlib_query(Params params) {
     static_cast<LCCommittedHit *>(params.out1)[i] = lc_ray_query_committed_hit(qa);
 }
 
+// ---- the same two RayQuery sites lowered INLINE (what plugin/hybrid/b200_ray_query_lowering.inl emits): the handler bodies sit in
+// the kernel's scope between proceed and resolve and use the kernel's own variables (`params`) instead of a capture struct
+extern "C" __global__ void k_devlib_query_inline(Params params) {
+    const lc_uint i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= params.n) return;
+    LCRay ray = params.rays[i];
+    LCRayQueryAll q = lc_accel_query_all(params.accel, ray, params.mask);
+    {// ray query #0, lowered inline
+        LCRayQueryInline lc_rq;
+        lc_ray_query_inline_begin(lc_rq, q);
+        while (lc_ray_query_inline_proceed(lc_rq)) {
+            LCIntersectionResult result{};
+            const LCRTCandidate &lc_rt_candidate = lc_rq.candidate;
+            if (lc_rq.triangle_candidate) {
+                LCTriangleHit h = LC_RAY_QUERY_TRIANGLE_CANDIDATE_HIT(q);
+                if (params.tri_prog == 0u) {
+                    LC_RAY_QUERY_COMMIT_TRIANGLE(q);
+                } else if (params.tri_prog == 1u) {
+                    if (h.m1 % 3u != 0u) { LC_RAY_QUERY_COMMIT_TRIANGLE(q); }
+                } else if (params.tri_prog == 3u) {
+                    LC_RAY_QUERY_COMMIT_TRIANGLE(q);
+                    LC_RAY_QUERY_TERMINATE(q);
+                }
+            } else {
+                LCProceduralHit h = LC_RAY_QUERY_PROCEDURAL_CANDIDATE_HIT(q);
+                LCRay wray = LC_RAY_QUERY_WORLD_RAY(q);
+                const float *b = params.aabbs + 6u * h.m1;
+                lc_float4x4 m = lc_accel_instance_transform(params.accel, h.m0);
+                const double cxo = 0.5 * ((double)b[0] + (double)b[3]), cyo = 0.5 * ((double)b[1] + (double)b[4]), czo = 0.5 * ((double)b[2] + (double)b[5]);
+                const double ro = 0.5 * ((double)b[3] - (double)b[0]);
+                const double cx = (double)m[0].x * cxo + (double)m[1].x * cyo + (double)m[2].x * czo + (double)m[3].x;
+                const double cy = (double)m[0].y * cxo + (double)m[1].y * cyo + (double)m[2].y * czo + (double)m[3].y;
+                const double cz = (double)m[0].z * cxo + (double)m[1].z * cyo + (double)m[2].z * czo + (double)m[3].z;
+                const double rad = ro * sqrt((double)m[0].x * m[0].x + (double)m[0].y * m[0].y + (double)m[0].z * m[0].z);
+                const double Lx = wray.m0[0] - cx, Ly = wray.m0[1] - cy, Lz = wray.m0[2] - cz;
+                const double dx = wray.m2[0], dy = wray.m2[1], dz = wray.m2[2];
+                const double a = dx * dx + dy * dy + dz * dz, hb = Lx * dx + Ly * dy + Lz * dz, cc = Lx * Lx + Ly * Ly + Lz * Lz - rad * rad;
+                const double disc = hb * hb - a * cc;
+                if (disc >= 0.0) {
+                    const double sq = sqrt(disc);
+                    const double t0 = (-hb - sq) / a, t1 = (-hb + sq) / a;
+                    if (t0 >= (double)wray.m1 && t0 < (double)wray.m3) {
+                        LC_RAY_QUERY_COMMIT_PROCEDURAL(q, (float)t0);
+                    } else if (t1 >= (double)wray.m1 && t1 < (double)wray.m3) {
+                        LC_RAY_QUERY_COMMIT_PROCEDURAL(q, (float)t1);
+                    }
+                }
+            }
+            lc_ray_query_inline_resolve(lc_rq, result);
+        }
+        lc_ray_query_inline_end(lc_rq, q);
+    }// ray query #0
+    static_cast<LCCommittedHit *>(params.out0)[i] = lc_ray_query_committed_hit(q);
+    LCRayQueryAny qa = lc_accel_query_any(params.accel, ray, params.mask);
+    {// ray query #1, lowered inline
+        LCRayQueryInline lc_rq;
+        lc_ray_query_inline_begin(lc_rq, qa);
+        while (lc_ray_query_inline_proceed(lc_rq)) {
+            LCIntersectionResult result{};
+            const LCRTCandidate &lc_rt_candidate = lc_rq.candidate;
+            if (lc_rq.triangle_candidate) {
+                LC_RAY_QUERY_COMMIT_TRIANGLE(qa);
+            } else {
+            }
+            lc_ray_query_inline_resolve(lc_rq, result);
+        }
+        lc_ray_query_inline_end(lc_rq, qa);
+    }// ray query #1
+    static_cast<LCCommittedHit *>(params.out1)[i] = lc_ray_query_committed_hit(qa);
+}
+
 // ---- in-kernel instance edits (cuda_device_resource.h:1470-1510): thread i edits instance i
 extern "C" __global__ void k_devlib_instance_ops(Params params) {
     const lc_uint i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -174,6 +246,12 @@ DL_EXPORT int dl_query(void *stream, uint64_t handle, void *instances, const voi
                        void *hits_all, void *hits_any) {
     if (n == 0) return 0;
     k_devlib_query<<<(n + 127u) / 128u, 128, 0, static_cast<cudaStream_t>(stream)>>>(make_params(handle, instances, rays, n, mask, hits_all, hits_any, aabbs, tri_prog));
+    return (int)cudaGetLastError();
+}
+DL_EXPORT int dl_query_inline(void *stream, uint64_t handle, void *instances, const void *rays, uint32_t n, uint32_t mask, const void *aabbs, uint32_t tri_prog,
+                              void *hits_all, void *hits_any) {
+    if (n == 0) return 0;
+    k_devlib_query_inline<<<(n + 127u) / 128u, 128, 0, static_cast<cudaStream_t>(stream)>>>(make_params(handle, instances, rays, n, mask, hits_all, hits_any, aabbs, tri_prog));
     return (int)cudaGetLastError();
 }
 DL_EXPORT int dl_instance_ops(void *stream, uint64_t handle, void *instances, uint32_t n, void *masks_out) {

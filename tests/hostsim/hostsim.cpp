@@ -361,4 +361,39 @@ void hs_query(const void *tlas, const void *instances, const void *rays_, uint64
     query_impl<LocalStore>(tlas, instances, rays_, n, masks, mask_stride, terminate_on_first, tri_prog, proc_prog, hits_);
 }
 
+// The same query with the candidate programs run by the CALLER between two steps (SuspendingCallbacks / Traversal::resolve): the
+// shape of the inline RayQuery lowering, `while (proceed) { handler }`.  Must produce what hs_query produces.
+void hs_query_suspending(const void *tlas, const void *instances_, const void *rays_, uint64_t n, const uint32_t *masks, int mask_stride,
+                         int terminate_on_first, uint32_t tri_prog, uint32_t proc_prog, void *hits_) {
+    const Ray *rays = static_cast<const Ray *>(rays_);
+    const Instance *instances = static_cast<const Instance *>(instances_);
+    CommittedHit *hits = static_cast<CommittedHit *>(hits_);
+    const BuiltinPrograms programs{tri_prog, proc_prog};
+    for (uint64_t i = 0; i < n; i++) {
+        LocalStore st;
+        SuspendingCallbacks cb;
+        cb.pend.kind = 0;
+        Traversal<MODE_QUERY, false, LocalStore, SuspendingCallbacks> tr;
+        tr.init(static_cast<const BlobHeader *>(tlas), instances, &rays[i], mask_stride ? masks[i] : masks[0], &st, &cb);
+        tr.terminate_on_first = terminate_on_first != 0;
+        while (tr.step()) {
+            if (!tr.candidate_pending()) continue;
+            const PendingCandidate pc = cb.pend;
+            const Ray wr = tr.candidate_ray();
+            CandidateResult r;
+            if (pc.kind == 1) {
+                r = programs.on_triangle(pc.inst, pc.prim, pc.u, pc.v, pc.t, wr);
+            } else {
+                const f4 *br = reinterpret_cast<const f4 *>(tr.prims + (uint64_t)pc.pi * sizeof(BoxRecord));
+                r = programs.on_procedural(pc.inst, pc.prim, wr, instances, br[0], br[1]);
+            }
+            tr.resolve(r.committed, r.terminated, r.t_hit);
+        }
+        CommittedHit h;
+        tr.result(h.inst, h.prim, h.hit_type, h.t, h.u, h.v);
+        if (h.hit_type == HIT_MISS) h.t = rays[i].tmax;
+        hits[i] = h;
+    }
+}
+
 }// extern "C"

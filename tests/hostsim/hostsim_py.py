@@ -43,6 +43,7 @@ def lib():
         L.hs_trace_closest.argtypes = [vp, vp, vp, u64, vp, ci, vp, vp]
         L.hs_trace_any.argtypes = [vp, vp, vp, u64, vp, ci, vp]
         L.hs_query.argtypes = [vp, vp, vp, u64, vp, ci, ci, u32, u32, vp]
+        L.hs_query_suspending.argtypes = [vp, vp, vp, u64, vp, ci, ci, u32, u32, vp]
         L.hs_set_defer.argtypes = [ci]
         _LIB = L
     return _LIB
@@ -151,9 +152,9 @@ class SimAccel:
         lib().hs_trace_any(_p(self.blob), _p(self.instances), _p(rays), len(rays), _p(m), ms, _p(out))
         return out
 
-    def query(self, rays, mask=0xFF, terminate_on_first=False, tri_prog=0, proc_prog=0):
+    def query(self, rays, mask=0xFF, terminate_on_first=False, tri_prog=0, proc_prog=0, suspending=False):
         rays = np.ascontiguousarray(rays)
         m, ms = self._masks(mask, len(rays))
         hits = np.zeros(len(rays), dtype=S.CHIT_DTYPE)
-        lib().hs_query(_p(self.blob), _p(self.instances), _p(rays), len(rays), _p(m), ms, int(terminate_on_first), tri_prog, proc_prog, _p(hits))
+        (lib().hs_query_suspending if suspending else lib().hs_query)(_p(self.blob), _p(self.instances), _p(rays), len(rays), _p(m), ms, int(terminate_on_first), tri_prog, proc_prog, _p(hits))
         return hits

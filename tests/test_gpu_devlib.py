@@ -28,6 +28,7 @@ def dl():
     vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
     L.dl_trace.argtypes = [vp, u64, vp, vp, u32, u32, vp, vp]
     L.dl_query.argtypes = [vp, u64, vp, vp, u32, u32, vp, u32, vp, vp]
+    L.dl_query_inline.argtypes = [vp, u64, vp, vp, u32, u32, vp, u32, vp, vp]
     L.dl_instance_ops.argtypes = [vp, u64, vp, u32, vp]
     return L
 
@@ -108,6 +109,21 @@ def test_ray_query_with_outlined_handlers(oracle, dev, dl):
         ga = lc.chits_to_numpy(h_any)
         ea = oa.query(rays, 0xFF, True, 0, 2)             # site #1: triangles commit, procedural candidates are ignored
         assert np.array_equal(ea["hit_type"] != 0, ga["hit_type"] != 0)
+        # the same two sites lowered inline (`while (proceed) { handler }`, handlers in the kernel's scope): the traversal is the
+        # same step by step, so query_all leaves identical records.  (A terminating handler and query_any keep the first hit that
+        # commits, and which lane gets there first depends on the phase vote of the outlined form: hit / miss only.)
+        i_all = torch.empty((n, 6), dtype=torch.int32, device="cuda")
+        i_any = torch.empty((n, 6), dtype=torch.int32, device="cuda")
+        rc = dl.dl_query_inline(torch.cuda.current_stream().cuda_stream, bh, bi, d_rays.data_ptr(), n, 0xFF, d_aabbs.data_ptr(), tri_prog,
+                                i_all.data_ptr(), i_any.data_ptr())
+        assert rc == 0
+        torch.cuda.synchronize()
+        gi, gia = lc.chits_to_numpy(i_all), lc.chits_to_numpy(i_any)
+        if tri_prog == 3:
+            assert np.array_equal(gi["hit_type"] != 0, g["hit_type"] != 0)
+        else:
+            assert gi.tobytes() == g.tobytes()
+        assert np.array_equal(gia["hit_type"] != 0, ga["hit_type"] != 0)
 
 
 def test_in_kernel_instance_accessors(oracle, dev, dl):

@@ -162,10 +162,16 @@ def test_ray_query(oracle):
         assert np.array_equal(e["prim"][hit], g["prim"][hit])
         np.testing.assert_allclose(g["t"][hit], e["t"][hit], rtol=1e-5)
         np.testing.assert_allclose(g["bary"][hit], e["bary"][hit], atol=1e-4)
+        # the same query with the handlers run by the caller between two steps (inline lowering): identical records
+        gs = sa.query(rays, 0xFF, False, tri_prog, 0, suspending=True)
+        assert gs.tobytes() == g.tobytes()
+    for tri_prog in (0, 3):
+        assert sa.query(rays, 0xFF, False, tri_prog, 1, suspending=True).tobytes() == sa.query(rays, 0xFF, False, tri_prog, 1).tobytes()
     # query_any: hit / miss only (D5)
     e = oa.query(rays, 0xFF, True, 0, 0)
     g = sa.query(rays, 0xFF, True, 0, 0)
     assert np.array_equal(e["hit_type"] != 0, g["hit_type"] != 0)
+    assert sa.query(rays, 0xFF, True, 0, 0, suspending=True).tobytes() == g.tobytes()
     # intersect() ignores procedural primitives
     got = sa.trace_closest(rays)
     assert not np.any(got["inst"] == 0)
