@@ -408,6 +408,8 @@ void lc_ray_query_trace(LCRayQuery &q, lc_uint impl_tag, void *ctx) noexcept {
     if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
 }
 
+//@inline-rayquery-api-begin  (plugin/hybrid keeps this section out of the embedded library text: its code generator emits it, in
+// front of the kernels that use it; the reference's embedded array has a fixed size, plugin/hybrid/make_device_resource.py)
 // ------------------------------------------------------------------------------------------ RayQuery, lowered inline
 // What the inline lowering of RayQueryStmt calls (plugin/hybrid/b200_ray_query_lowering.inl emits it when the codegen is told
 // to; SURVEY.md 7.7, the shape of src/backends/common/hlsl/hlsl_codegen.cpp:555-567):
@@ -470,3 +472,4 @@ __device__ inline void lc_ray_query_inline_end(LCRayQueryInline &s, LCRayQuery &
     s.tr.result(q.hit.m0, q.hit.m1, q.hit.m3, q.hit.m4, q.hit.m2.x, q.hit.m2.y);
     if (q.hit.m3 == static_cast<lc_uint>(LCHitType::MISS)) q.hit.m0 = ~0u;
 }
+//@inline-rayquery-api-end

@@ -17,6 +17,7 @@
 //
 // Together with b200_optix_stub.cpp (an `optix::api()` that never opens libnvoptix) `lc-backend-b200` starts and runs on a
 // machine without OptiX.
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 
@@ -87,8 +88,15 @@ CUDAShaderOptiX::CUDAShaderOptiX(optix::DeviceContext, luisa::vector<std::byte> 
     auto s = luisa::new_with_allocator<NativeRT>();
     s->block_size = metadata.block_size;
     auto load = [&](const void *text, size_t size) noexcept {
+        // Register cap: the reference hands kernels that trace rays to OptiX, which compiles them for at most 128 registers
+        // per thread unless told otherwise (module_compile_options.maxRegisterCount, cuda_shader_optix.cpp:109-112); the plain
+        // JIT has no such default and gives a path tracer 170+, i.e. one 256-thread block per SM (C5 through this backend:
+        // 432 spp/s with OptiX's cap, 278 without; profiles/r2_native_launch.md).  Same rule here.
         CUlinkState link{};
-        LUISA_CHECK_CUDA(cuLinkCreate(0u, nullptr, nullptr, &link));
+        CUjit_option jit_options[] = {CU_JIT_MAX_REGISTERS};
+        void *jit_values[] = {reinterpret_cast<void *>(static_cast<uintptr_t>(
+            metadata.max_register_count == 0u ? 128u : std::clamp(metadata.max_register_count, 16u, 255u)))};
+        LUISA_CHECK_CUDA(cuLinkCreate(1u, jit_options, jit_values, &link));
         auto ret = cuLinkAddData(link, CU_JIT_INPUT_PTX, const_cast<void *>(text), size, "rt_kernel.ptx", 0u, nullptr, nullptr);
         if (ret != CUDA_SUCCESS) {
             LUISA_CHECK_CUDA(cuLinkDestroy(link));

@@ -30,7 +30,8 @@ rt=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/b200_cuda_rt.o#;
 # the code generator with this repository's RayQuery lowering (inline `while (proceed) { handler }` loops; the reference's outlined
 # form stays available behind LUISA_B200_RAY_QUERY=outline): a build-time copy of cuda_codegen_ast.cpp, see make_codegen.py
 python "$HERE/make_codegen.py" "$REF/src/backends/cuda/cuda_codegen_ast.cpp" "$HERE/b200_ray_query_lowering.inl" "$W/b200_codegen_ast.cpp"
-cg=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/b200_codegen_ast.o#; s# -c [^ ]*cuda_accel\.cpp# -I$REF/src/backends/cuda -c $W/b200_codegen_ast.cpp#; s# -MD -MT [^ ]* -MF [^ ]*##")
+python "$HERE/make_device_resource.py" --inline-api "$W/b200_inline_api.inc"   # lc_ray_query_inline_* as text, emitted by the lowering
+cg=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/b200_codegen_ast.o#; s# -c [^ ]*cuda_accel\.cpp# -I$REF/src/backends/cuda -I$W -c $W/b200_codegen_ast.cpp#; s# -MD -MT [^ ]* -MF [^ ]*##")
 (cd "$BD" && eval "$cg")
 for unit in b200_shader_rt b200_optix_stub; do
   one=$(echo "$cmd" | sed -E "s# -o [^ ]*cuda_accel\.cpp\.o# -o $W/$unit.o#; s# -c [^ ]*cuda_accel\.cpp# -I$REF/src/backends/cuda -I$ROOT/include -c $HERE/$unit.cpp#; s# -MD -MT [^ ]* -MF [^ ]*##")
