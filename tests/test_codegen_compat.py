@@ -39,11 +39,19 @@ def _compile(src: bytes):
     return res[0], log.decode(errors="replace"), ptx.decode(errors="replace")
 
 
-@pytest.mark.parametrize("kernel", ["closest", "any", "query"])
+@pytest.mark.parametrize("kernel", ["closest", "any", "query", "query_inline"])
 def test_generated_kernel_compiles_against_spliced_library(kernel):
     import splice_device_library as SP
     library = "".join(open(os.path.join(REF_LIB, h)).read() for h in ("cuda_device_half.h", "cuda_device_math.h", "cuda_device_resource.h"))
-    spliced = SP.splice(library, SP.library_text())
+    rt_library = SP.library_text()
+    if kernel == "query_inline":
+        # emitted by THIS repository's RayQuery lowering (plugin/hybrid/b200_ray_query_lowering.inl, LUISA_B200_RAY_QUERY=inline): the
+        # generator itself emits the lc_ray_query_inline_* section behind the library, which therefore comes without it
+        sys.path.insert(0, os.path.join(ROOT, "plugin", "hybrid"))
+        import make_device_resource as MDR
+        rt_library, api = MDR.cut_inline_api(rt_library)
+        assert "lc_ray_query_inline_proceed" in api and "lc_ray_query_inline_proceed" not in rt_library
+    spliced = SP.splice(library, rt_library)
     assert "_optix_hitobject_traverse," in library and "_optix_hitobject_traverse," not in spliced     # the asm call is gone
     gen = open(os.path.join(ROOT, "tests", "golden", "codegen", kernel + ".cu")).read()
     src = gen.replace("/* built-in device library */", spliced)
@@ -55,3 +63,5 @@ def test_generated_kernel_compiles_against_spliced_library(kernel):
     assert not re.findall(r"_optix_[a-z_0-9]+", ptx)
     assert "%ctaid" in ptx and "%tid" in ptx
     assert "__intersection__ray_query" not in ptx and "__anyhit__ray_query" not in ptx
+    if kernel == "query_inline":
+        assert "lc_ray_query_inline_begin(lc_rq" in gen and "lc_ray_query_trace(" not in gen.split("/* built-in device library */")[1].split("inline RayQuery API end")[1]

@@ -69,9 +69,9 @@ def test_reference_test_programs_render_the_same_image(tmp_path):
         if "image_optix_launch" in e:
             assert e["image_optix_launch"]["pixels_differing_by_more_than_2"] <= tol_optix, (test, e["image_optix_launch"])
         if "procedural" in test:
-            # RayQuery handlers lowered inline (`while (proceed) { handler }`, this repository's RayQueryLowering) and the
-            # reference's outlined handlers (LUISA_B200_RAY_QUERY=outline) run the same traversal and the same handler arithmetic...
-            assert e["b200_outlined"]["rc"] == 0, e["b200_outlined"]
+            # RayQuery handlers lowered inline (`while (proceed) { handler }`, this repository's RayQueryLowering,
+            # LUISA_B200_RAY_QUERY=inline) and the reference's outlined handlers run the same traversal and the same handler arithmetic...
+            assert e["b200_inline"]["rc"] == 0, e["b200_inline"]
             # ...but not the same compiler schedule: the handler's `d <= radius` flips on FMA contraction (see above), so a few
             # silhouette pixels may differ between the two forms as they do between b200 and b200o
             assert e["image_inline_vs_outlined_lowering"]["pixels_differing"] <= 1600, e["image_inline_vs_outlined_lowering"]

@@ -70,16 +70,16 @@ def main():
             res[test] = {"unavailable": "not built"}
             continue
         imgs, entry = {}, {}
-        # b200 emits RayQuery handlers inline (plugin/hybrid/b200_ray_query_lowering.inl); `b200_outlined` is the same backend told to
-        # keep the reference's outlined handlers (LUISA_B200_RAY_QUERY=outline): only programs with a RayQuery differ
-        backends = ("cuda", "b200") + (("b200_outlined",) if "procedural" in test else ()) + \
+        # `b200_inline` is b200 told to lower RayQuery handlers inline (LUISA_B200_RAY_QUERY=inline, plugin/hybrid/b200_ray_query_lowering.inl)
+        # instead of outlining them as the reference does: only programs with a RayQuery differ
+        backends = ("cuda", "b200") + (("b200_inline",) if "procedural" in test else ()) + \
                    (("b200o",) if os.path.exists(os.path.join(BIN, "liblc-backend-b200o.so")) else ())
         for backend in backends:
             d = os.path.join("/tmp", f"lc_{test}_{backend}")
             os.makedirs(d, exist_ok=True)
             t0 = time.time()
-            benv = dict(env, LUISA_B200_RAY_QUERY="outline") if backend == "b200_outlined" else env
-            r = subprocess.run([exe, backend.replace("_outlined", "")], cwd=d, capture_output=True, text=True, timeout=900, env=benv)
+            benv = dict(env, LUISA_B200_RAY_QUERY="inline") if backend == "b200_inline" else env
+            r = subprocess.run([exe, backend.replace("_inline", "")], cwd=d, capture_output=True, text=True, timeout=900, env=benv)
             entry[backend] = {"rc": r.returncode, "wall_s": time.time() - t0}
             for line in (r.stdout + r.stderr).splitlines():
                 if "Time:" in line or "time" in line.lower() and "ms" in line:
@@ -91,8 +91,8 @@ def main():
                 subprocess.run(["cp", png, os.path.join(ROOT, "gpurun_out", f"{test}_{backend}.png")])
             else:
                 entry[backend]["log_tail"] = (r.stdout + r.stderr)[-600:]
-        if "b200" in imgs and "b200_outlined" in imgs:
-            diff = np.abs(imgs["b200"] - imgs["b200_outlined"])
+        if "b200" in imgs and "b200_inline" in imgs:
+            diff = np.abs(imgs["b200"] - imgs["b200_inline"])
             entry["image_inline_vs_outlined_lowering"] = {"max_abs_diff": int(diff.max()), "pixels_differing": int((diff.max(axis=2) > 0).sum())}
         for other, key in (("b200", "image"), ("b200o", "image_optix_launch")):
             if "cuda" in imgs and other in imgs:
