@@ -140,6 +140,13 @@ class HitGatherer:
         return None if self.full is None else self.full.view(-1, self.words)
 
 
+def peer_tile_layout(rank: int, world: int, tile: int = TILE, record_bytes: int = 24):
+    """(byte offset of this rank's local tile 0, byte stride between its consecutive local tiles) in a ray-ordered framebuffer of
+    `record_bytes` records when tiles of `tile` rays are dealt round-robin: local tile t of rank r is global tile t * world + r."""
+    tile_bytes = tile * record_bytes
+    return rank * tile_bytes, world * tile_bytes
+
+
 class _RawCudaBuffer:
     """A device address as something torch.as_tensor understands (int32 view of `words` elements)."""
 
@@ -186,8 +193,8 @@ class PeerFramebuffer:
             _check(lib().lcbFramebufferOpen(device._h, hb, C.byref(addr)), "lcbFramebufferOpen")
         self.address = int(addr.value)
         self.tile_bytes = tile * words * 4
-        self.base = self.address + self.rank * self.tile_bytes          # where this rank's local tile 0 goes
-        self.stride = self.world * self.tile_bytes
+        offset, self.stride = peer_tile_layout(self.rank, self.world, tile, words * 4)
+        self.base = self.address + offset                               # where this rank's local tile 0 goes
         # the owner's view of the whole buffer, ray order
         self.full = torch.as_tensor(_RawCudaBuffer(self.address, self.bytes // 4), device=tdev).view(-1, words) if self.owner else None
 

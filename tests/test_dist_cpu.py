@@ -68,3 +68,21 @@ def test_broadcast_and_gather_gloo_world2():
     ret = mgr.dict()
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret[0] and ret[1]
+
+
+def test_peer_framebuffer_layout_is_ray_order():
+    """The (base, stride) every rank stores with (dist.peer_tile_layout, used by PeerFramebuffer / lcrtTraceClosestTiled) puts
+    record i of a tile-sharded batch where ray order wants it — the same order dist.gather_hits produces."""
+    from luisacompute_b200 import dist as D
+    tile, world, n_local_tiles, rec = 8, 3, 5, 24
+    n = tile * world * n_local_tiles
+    fb = np.full(n * rec, 0xFF, dtype=np.uint8)
+    for r in range(world):
+        idx = D.ray_indices_for_rank(n, r, world, tile)
+        base, stride = D.peer_tile_layout(r, world, tile, rec)
+        for i_local, ray in enumerate(idx):
+            t, k = divmod(i_local, tile)
+            off = base + t * stride + k * rec                      # the address computation of HitDest::at (lcrt_kernels.cu)
+            fb[off:off + rec] = np.frombuffer(np.uint64(ray).tobytes() * 3, dtype=np.uint8)
+    got = fb.view(np.uint64).reshape(n, 3)
+    assert np.array_equal(got[:, 0], np.arange(n, dtype=np.uint64)) and np.array_equal(got[:, 2], np.arange(n, dtype=np.uint64))
