@@ -779,6 +779,7 @@ struct TraceSmem {
     u2 stack[TRACE_SMEM_STACK * TRACE_BLOCK];
     f4 rows[2 * TRACE_BLOCK];
     uint32_t words[CW_COUNT * TRACE_BLOCK];
+    uint32_t slots[(TRACE_BLOCK / 32) * 4];// FUSED_BATCH, per warp: batch index of slot 0, of slot 1 (~0 = free), rays still missing (16 bits each)
 };
 __device__ __forceinline__ TraceSmem *trace_smem() {
     // dynamic shared memory (sizeof(TraceSmem) at launch): referencing the array directly keeps every access an
@@ -838,7 +839,6 @@ struct TraceParams {
     int terminate_on_first;
     uint32_t magic;              // PLANT_MAGIC, see plant_byte()
     HitDest dest;                // FUSED kernels: where the final records go
-    int stage;                   // FUSED kernels: collect the records of a batch before storing them (else every record on its own)
 };
 
 // Persistent threads: every warp reserves TRACE_BATCH consecutive rays per atomic and hands them to its idle lanes
@@ -849,7 +849,9 @@ struct TraceParams {
 // (in p.out, the local scratch array) and stored where HitDest says when the batch is complete — a framebuffer that may live in a peer GPU's memory.
 // The stores then leave over NVLink while the kernel is still tracing, spread over its whole duration (not in one burst from a
 // second pass: eight ranks storing into one at the same moment queue at its NVLink ingress), in 512-byte warp stores.
-template<int MODE, bool COUNT, class Callbacks, bool FUSED = false>
+// FUSED: 0 provisional records + k_refine_hits; 1 every final record stored as its ray ends; 2 final records stored per complete batch
+enum : int { FUSED_NONE = 0, FUSED_EACH = 1, FUSED_BATCH = 2 };
+template<int MODE, bool COUNT, class Callbacks, int FUSED = FUSED_NONE>
 __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(TraceParams p) {
     HybridStore store;
     Callbacks cb;
@@ -873,16 +875,21 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
     unsigned long long c_nodes = 0, c_prims = 0, c_insts = 0, c_exact = 0;
     bool exhausted = false;
     uint32_t denied = 0u;// consecutive iterations in which lanes with a pending primitive were made to wait (warp-uniform)
-    // FUSED: the batches whose records are being staged (warp-uniform): first ray, rays in the batch, rays still missing
-    uint64_t slot_base[STAGE_SLOTS] = {};
-    uint32_t slot_count[STAGE_SLOTS] = {}, slot_left[STAGE_SLOTS] = {};
+    // FUSED_BATCH: the batches whose records are being collected (warp-uniform): index of the batch (first ray / TRACE_BATCH, ~0 =
+    // slot free) and, 16 bits per slot, the rays still missing
+    // (kept in shared memory, three words per warp, read at refills only: as registers they spilled traversal state in the hot loop)
+    static_assert(STAGE_SLOTS == 2u && TRACE_BATCH < 65536u, "slot bookkeeping");
+    volatile uint32_t *slot = trace_smem()->slots + (threadIdx.x >> 5) * 4u;
+    if constexpr (FUSED == FUSED_BATCH) {
+        if (lane == 0u) slot[0] = ~0u, slot[1] = ~0u, slot[2] = 0u;
+        __syncwarp();
+    }
     for (;;) {
         // ---- warp-cooperative retire + refill of idle lanes
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
         if (idle && ((!exhausted && (uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN) || idle == 0xffffffffu)) {
-            if constexpr (MODE == MODE_CLOSEST && FUSED) {
-                // finished records go to the staging slot of their batch; a batch without a slot (both were busy when it was
-                // reserved) is stored record by record
+            if constexpr (MODE == MODE_CLOSEST && FUSED != FUSED_NONE) {
+                // the retiring lanes finish their records themselves (exact t, u, v)
                 uint64_t ray_idx = ~0ull;
                 uint2 r0 = make_uint2(0u, 0u), r1 = r0, r2 = r0;
                 if (unsaved) {
@@ -893,31 +900,43 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                     r0 = make_uint2(tr.hit_inst(), prim), r1 = make_uint2(as_uint(u), as_uint(v)), r2 = make_uint2(as_uint(t), 0u);
                 }
                 bool staged = false;
+                if constexpr (FUSED == FUSED_BATCH) {
+                    // records go to their batch's place in the local scratch array; a batch without a slot (both were busy when it
+                    // was reserved) is stored record by record
+                    const uint32_t my_batch = unsaved ? (uint32_t)(ray_idx / TRACE_BATCH) : ~0u - 1u;
 #pragma unroll
-                for (uint32_t sl = 0; sl < STAGE_SLOTS; sl++) {
-                    const bool mine = unsaved && slot_left[sl] != 0u && ray_idx >= slot_base[sl] && ray_idx < slot_base[sl] + slot_count[sl];
-                    const uint32_t m = __ballot_sync(0xffffffffu, mine);
-                    if (m == 0u) continue;
-                    uint2 *st = reinterpret_cast<uint2 *>(static_cast<char *>(p.out) + slot_base[sl] * 24u);
-                    if (mine) {
-                        uint2 *e = st + (uint32_t)(ray_idx - slot_base[sl]) * 3u;
-                        e[0] = r0, e[1] = r1, e[2] = r2;
-                        staged = true;
-                    }
-                    slot_left[sl] -= (uint32_t)__popc(m);
-                    if (slot_left[sl] == 0u) {
-                        // the batch is complete: its records are consecutive in the destination (a batch never straddles a tile)
-                        __syncwarp();
-                        char *dst = reinterpret_cast<char *>(p.dest.at(p.out, slot_base[sl]));
-                        const uint32_t bytes = slot_count[sl] * 24u;
-                        if (dst != reinterpret_cast<char *>(st)) {
-                            if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(st) | bytes) & 15u) == 0u) {
-                                const uint4 *src = reinterpret_cast<const uint4 *>(st);
-                                for (uint32_t k = lane; k < bytes / 16u; k += 32u) __stcs(reinterpret_cast<uint4 *>(dst) + k, __ldcg(src + k));
-                            } else {
-                                for (uint32_t k = lane; k < bytes / 8u; k += 32u) __stcs(reinterpret_cast<uint2 *>(dst) + k, __ldcg(st + k));
-                            }
+                    for (uint32_t sl = 0; sl < STAGE_SLOTS; sl++) {
+                        const uint32_t sb = slot[sl];
+                        const bool mine = my_batch == sb;
+                        const uint32_t m = __ballot_sync(0xffffffffu, mine);
+                        if (m == 0u) continue;
+                        const uint64_t base = (uint64_t)sb * TRACE_BATCH;
+                        uint2 *st = reinterpret_cast<uint2 *>(static_cast<char *>(p.out) + base * 24u);
+                        if (mine) {
+                            uint2 *e = st + (uint32_t)(ray_idx - base) * 3u;
+                            e[0] = r0, e[1] = r1, e[2] = r2;
+                            staged = true;
                         }
+                        const uint32_t left = slot[2] - ((uint32_t)__popc(m) << (16u * sl));
+                        __syncwarp();
+                        if (lane == 0u) slot[2] = left;
+                        if (((left >> (16u * sl)) & 0xffffu) == 0u) {
+                            // the batch is complete: its records are consecutive in the destination (a batch never straddles a tile)
+                            __syncwarp();
+                            char *dst = reinterpret_cast<char *>(p.dest.at(p.out, base));
+                            const uint64_t left_in_launch = p.n - base;
+                            const uint32_t bytes = (uint32_t)(left_in_launch < TRACE_BATCH ? left_in_launch : TRACE_BATCH) * 24u;
+                            if (dst != reinterpret_cast<char *>(st)) {
+                                if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(st) | bytes) & 15u) == 0u) {
+                                    const uint4 *src = reinterpret_cast<const uint4 *>(st);
+                                    for (uint32_t k = lane; k < bytes / 16u; k += 32u) __stcs(reinterpret_cast<uint4 *>(dst) + k, __ldcg(src + k));
+                                } else {
+                                    for (uint32_t k = lane; k < bytes / 8u; k += 32u) __stcs(reinterpret_cast<uint2 *>(dst) + k, __ldcg(st + k));
+                                }
+                            }
+                            if (lane == 0u) slot[sl] = ~0u;
+                        }
+                        __syncwarp();
                     }
                 }
                 if (unsaved && !staged) {
@@ -958,14 +977,15 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
                 base = __shfl_sync(0xffffffffu, base, 0);
                 warp_next = base < p.n ? base : p.n;
                 warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
-                if constexpr (MODE == MODE_CLOSEST && FUSED) {
-                    if (warp_next != warp_end && p.stage) {
-#pragma unroll
-                        for (uint32_t sl = 0; sl < STAGE_SLOTS; sl++)
-                            if (slot_left[sl] == 0u) {
-                                slot_base[sl] = warp_next, slot_count[sl] = slot_left[sl] = (uint32_t)(warp_end - warp_next);
-                                break;
-                            }
+                if constexpr (MODE == MODE_CLOSEST && FUSED == FUSED_BATCH) {
+                    if (warp_next != warp_end) {
+                        const uint32_t cnt = (uint32_t)(warp_end - warp_next), s0 = slot[0], s1 = slot[1], left = slot[2];
+                        __syncwarp();
+                        if (lane == 0u) {
+                            if (s0 == ~0u) slot[0] = (uint32_t)(warp_next / TRACE_BATCH), slot[2] = (left & 0xffff0000u) | cnt;
+                            else if (s1 == ~0u) slot[1] = (uint32_t)(warp_next / TRACE_BATCH), slot[2] = (left & 0x0000ffffu) | (cnt << 16);
+                        }
+                        __syncwarp();
                     }
                 }
 #if LCRT_PREFETCH_RAYS
@@ -1265,7 +1285,6 @@ static int trace_generic(cudaStream_t stream, const void *tlas, const void *inst
     static const bool force_fused = getenv("LCRT_FUSED_REFINE") != nullptr && atoi(getenv("LCRT_FUSED_REFINE")) != 0;
     const bool fused = MODE == MODE_CLOSEST && counters == nullptr && (dest.dst != nullptr || force_fused);
     p.dest = dest;
-    p.stage = stage ? 1 : 0;
     auto launch = [&](auto kernel, size_t smem) -> int {
         int bps = 0;
         LCRT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kernel, TRACE_BLOCK, smem));
@@ -1280,9 +1299,10 @@ static int trace_generic(cudaStream_t stream, const void *tlas, const void *inst
         return LCRT_SUCCESS;
     };
     int rc;
-    if (counters) rc = launch(k_trace<MODE, true, Callbacks, false>, sizeof(TraceSmem));
-    else if (fused) rc = launch(k_trace<MODE, false, Callbacks, MODE == MODE_CLOSEST>, sizeof(TraceSmem));
-    else rc = launch(k_trace<MODE, false, Callbacks, false>, sizeof(TraceSmem));
+    if (counters) rc = launch(k_trace<MODE, true, Callbacks, FUSED_NONE>, sizeof(TraceSmem));
+    else if (fused && stage && n / TRACE_BATCH < 0xfffffff0ull) rc = launch(k_trace<MODE, false, Callbacks, MODE == MODE_CLOSEST ? FUSED_BATCH : FUSED_NONE>, sizeof(TraceSmem));
+    else if (fused) rc = launch(k_trace<MODE, false, Callbacks, MODE == MODE_CLOSEST ? FUSED_EACH : FUSED_NONE>, sizeof(TraceSmem));
+    else rc = launch(k_trace<MODE, false, Callbacks, FUSED_NONE>, sizeof(TraceSmem));
     if (rc != LCRT_SUCCESS) return rc;
     if (MODE != MODE_ANY && !fused) {
         k_refine_hits<MODE><<<(uint32_t)((n + 255u) / 256u), 256, 0, stream>>>(p.tlas, p.rays, out, n, dest);

@@ -205,7 +205,9 @@ class PeerFramebuffer:
         ranks write into the owner, and one by one as the rays end otherwise: single 24-byte stores cost the kernel less, but
         eight GPUs sending them into one use its NVLink ingress badly (profiles/r2_scaling.md)."""
         if store_each_record is None:
-            store_each_record = self.world <= 2
+            import os
+            forced = os.environ.get("LCB200_PEER_STORE")     # developer knob: each | batch
+            store_each_record = forced == "each" if forced in ("each", "batch") else self.world <= 2
         return accel.trace_closest_tiled(rays, self.base + first_local_tile * self.stride, self.tile, self.stride, mask=mask, scratch=scratch,
                                          store_each_record=store_each_record)
 
