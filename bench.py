@@ -7,7 +7,7 @@ Workload (BASELINE.json configs[1], "C2"): displaced icosphere level 8 (1 310 72
   e2e        the same step through the public host-buffer call (Accel.trace_closest_host -> lcbTraceClosestHost): rays in
              pinned host memory, hits back in pinned host memory, copies inside the timed region
   roofline   dominant kernel = k_trace<closest> on the incoherent batch; algorithmic bytes per ray =
-             32 (ray) + 24 (hit) + nodes*80 + prims*48 + instances*128 with the per-ray averages COUNTED by the
+             32 (ray) + 24 (hit) + nodes*80 + prims*48 + instances*80 (the 80 bytes of a 256-byte instance record the traversal loads) with the per-ray averages COUNTED by the
              instrumented variant of the same kernel; peak = MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the oracle (CPU restatement of the reference's Embree-backed path) on all host cores, bounded sample
 `--impl reference` times that CPU path alone on the same workload definition.
