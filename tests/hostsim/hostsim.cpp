@@ -396,4 +396,94 @@ void hs_query_suspending(const void *tlas, const void *instances_, const void *r
     }
 }
 
+// The batch kernel's warp schedule (k_trace, lcrt_kernels.cu) replayed lane by lane: `warps` warps of 32 lanes share one ray
+// cursor, reserve 128 rays at a time, refill idle lanes when at least 12 are idle, advance every live lane by one node step per
+// iteration and run the primitive phase only when `vote` lanes (or every live lane) wait for it.  Returns the largest number
+// of iterations in a row that a lane with a pending primitive was made to wait (the quantity LCRT_TRI_VOTE_PATIENCE bounds
+// on the device), or -1 if a warp exceeds `max_iterations` (a lane starves: the schedule is not live).
+long long hs_query_warp_schedule(const void *tlas, const void *instances_, const void *rays_, uint64_t n, uint32_t mask, int terminate_on_first,
+                                 uint32_t tri_prog, uint32_t proc_prog, void *hits_, uint32_t warps, uint32_t vote, uint32_t refill_min,
+                                 uint64_t max_iterations) {
+    const Ray *rays = static_cast<const Ray *>(rays_);
+    const Instance *instances = static_cast<const Instance *>(instances_);
+    CommittedHit *hits = static_cast<CommittedHit *>(hits_);
+    struct Lane {
+        LocalStore st;
+        BuiltinPrograms cb;
+        Traversal<MODE_QUERY, false, LocalStore, BuiltinPrograms> tr;
+        bool active = false, unsaved = false;
+        uint64_t ray = 0;
+    };
+    struct Warp {
+        std::vector<Lane> lane;
+        uint64_t next = 0, end = 0, iterations = 0;
+        bool exhausted = false, finished = false;
+        uint32_t denied = 0;
+    };
+    std::vector<Warp> w(warps);
+    for (auto &x : w) x.lane.resize(32);
+    uint64_t cursor = 0;
+    long long worst = 0;
+    uint32_t running = warps;
+    while (running) {
+        for (auto &x : w) {
+            if (x.finished) continue;
+            if (++x.iterations > max_iterations) return -1;
+            uint32_t idle = 0;
+            for (int l = 0; l < 32; l++) idle += x.lane[l].active ? 0u : 1u;
+            if (idle && ((!x.exhausted && idle >= refill_min) || idle == 32u)) {
+                for (auto &L : x.lane)
+                    if (L.unsaved) {
+                        CommittedHit h;
+                        L.tr.result(h.inst, h.prim, h.hit_type, h.t, h.u, h.v);
+                        if (h.hit_type == HIT_MISS) h.t = rays[L.ray].tmax;
+                        hits[L.ray] = h;
+                        L.unsaved = false;
+                    }
+                if (x.exhausted) {
+                    x.finished = true, running--;
+                    continue;
+                }
+                if (x.next == x.end) {
+                    const uint64_t base = cursor;
+                    cursor += 128;
+                    x.next = base < n ? base : n, x.end = base + 128 < n ? base + 128 : n;
+                    if (x.next == x.end) x.exhausted = true;
+                }
+                const uint64_t avail = x.end - x.next;
+                uint32_t rank = 0;
+                for (auto &L : x.lane) {
+                    if (L.active) continue;
+                    if (rank < avail) {
+                        L.ray = x.next + rank;
+                        L.cb = BuiltinPrograms{tri_prog, proc_prog};
+                        L.tr.init(static_cast<const BlobHeader *>(tlas), instances, &rays[L.ray], mask, &L.st, &L.cb);
+                        L.tr.terminate_on_first = terminate_on_first != 0;
+                        L.active = true;
+                    }
+                    rank++;
+                }
+                x.next += idle < avail ? idle : avail;
+            }
+            bool alive[32];
+            uint32_t am = 0, pm = 0;
+            for (int l = 0; l < 32; l++) {
+                alive[l] = x.lane[l].active && x.lane[l].tr.step_node();
+                if (alive[l]) am++;
+                if (alive[l] && x.lane[l].tr.prim_pending()) pm++;
+            }
+            if (pm >= vote || pm == am) {
+                for (int l = 0; l < 32; l++) alive[l] = alive[l] && x.lane[l].tr.step_prim();
+                x.denied = 0;
+            } else if (pm) {
+                x.denied++;
+                if ((long long)x.denied > worst) worst = x.denied;
+            }
+            for (int l = 0; l < 32; l++)
+                if (x.lane[l].active && !alive[l]) x.lane[l].active = false, x.lane[l].unsaved = true;
+        }
+    }
+    return worst;
+}
+
 }// extern "C"

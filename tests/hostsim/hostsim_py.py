@@ -44,6 +44,8 @@ def lib():
         L.hs_trace_any.argtypes = [vp, vp, vp, u64, vp, ci, vp]
         L.hs_query.argtypes = [vp, vp, vp, u64, vp, ci, ci, u32, u32, vp]
         L.hs_query_suspending.argtypes = [vp, vp, vp, u64, vp, ci, ci, u32, u32, vp]
+        L.hs_query_warp_schedule.restype = C.c_longlong
+        L.hs_query_warp_schedule.argtypes = [vp, vp, vp, u64, u32, ci, u32, u32, vp, u32, u32, u32, u64]
         L.hs_set_defer.argtypes = [ci]
         _LIB = L
     return _LIB
@@ -151,6 +153,16 @@ class SimAccel:
         out = np.zeros(len(rays), dtype=np.uint32)
         lib().hs_trace_any(_p(self.blob), _p(self.instances), _p(rays), len(rays), _p(m), ms, _p(out))
         return out
+
+    def query_warp_schedule(self, rays, mask=0xFF, terminate_on_first=False, tri_prog=0, proc_prog=0, warps=8, vote=4, refill_min=12,
+                            max_iterations=1 << 24):
+        """The query through a lane-by-lane replay of the batch kernel's warp schedule.  Returns (hits, longest wait of a lane with
+        a pending primitive in iterations; -1 if a warp exceeded max_iterations)."""
+        rays = np.ascontiguousarray(rays)
+        hits = np.zeros(len(rays), dtype=S.CHIT_DTYPE)
+        worst = lib().hs_query_warp_schedule(_p(self.blob), _p(self.instances), _p(rays), len(rays), int(mask), int(terminate_on_first), tri_prog,
+                                             proc_prog, _p(hits), warps, vote, refill_min, max_iterations)
+        return hits, int(worst)
 
     def query(self, rays, mask=0xFF, terminate_on_first=False, tri_prog=0, proc_prog=0, suspending=False):
         rays = np.ascontiguousarray(rays)

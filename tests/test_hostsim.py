@@ -172,6 +172,13 @@ def test_ray_query(oracle):
     g = sa.query(rays, 0xFF, True, 0, 0)
     assert np.array_equal(e["hit_type"] != 0, g["hit_type"] != 0)
     assert sa.query(rays, 0xFF, True, 0, 0, suspending=True).tobytes() == g.tobytes()
+    # the batch kernel's warp schedule replayed lane by lane (refill at 12 idle lanes, primitive phase on a vote of 4): the same
+    # records, and no lane with a pending primitive waits anywhere near the device's patience bound (LCRT_TRI_VOTE_PATIENCE = 128)
+    ref = sa.query(rays, 0xFF, False, 1, 0)
+    for warps in (1, 37):
+        gw, worst = sa.query_warp_schedule(rays, tri_prog=1, warps=warps, max_iterations=1 << 20)
+        assert worst >= 0, "a warp of the replayed schedule did not finish: a lane starves"
+        assert gw.tobytes() == ref.tobytes() and worst < 64, worst
     # intersect() ignores procedural primitives
     got = sa.trace_closest(rays)
     assert not np.any(got["inst"] == 0)
