@@ -28,3 +28,14 @@ def oracle():
     from oracle import oracle_py
     oracle_py.lib()
     return oracle_py
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Tie / grazing counts of every closest-hit comparison of the run (tests/gpu_util.py SOFT_LOG)."""
+    mod = sys.modules.get("tests.gpu_util")
+    log = getattr(mod, "SOFT_LOG", None) if mod else None
+    if not log:
+        return
+    terminalreporter.write_sep("-", "closest-hit comparisons against the oracle: rays / exact ids / inside the tie band / grazing (allowed)")
+    for what, n, exact, tie, grazing, allowed in log:
+        terminalreporter.write_line(f"{what:60s} {n:9d} {exact:9d} {tie:6d} {grazing:6d}  ({allowed})")

@@ -30,9 +30,21 @@ def build_pair(oracle, dev, geoms, affines, blas_index=None, masks=None, opaque=
     return oa, da, dm
 
 
+# what every closest-hit comparison of the run found inside the tolerance bands (the BASELINE.json rule allows ids to differ when the
+# two nearest hits are within 1e-5 relative t, and a hit whose exact barycentric is within 1e-4 of an edge): tests/conftest.py prints
+# the table at the end of the run, so the counts are on record and not just below a threshold
+SOFT_LOG = []
+
+
+def record_soft(what: str, res: dict, allowed) -> None:
+    SOFT_LOG.append((what, int(res.get("n", 0)), int(res.get("exact", 0)), int(res.get("tie", 0)), int(res.get("grazing", 0)), allowed))
+
+
 def check_closest(oracle, oa, da, rays, mask=0xFF, allow_soft=0):
+    import inspect
     got = lc.hits_to_numpy(da.trace_closest(rays, mask))
     res = oracle.compare_closest(oa, rays, got, mask)
+    record_soft(f"{inspect.stack()[1].function} mask " + (f"{int(mask):#x}" if isinstance(mask, (int, np.integer)) else "per ray"), res, allow_soft)
     assert res["id_mismatch"] == 0, res
     assert res["t_bad"] == 0 and res["bary_bad"] == 0, res
     assert res["tie"] + res["grazing"] <= allow_soft, res

@@ -40,6 +40,8 @@ def _closest(oracle, oa, da, rays, mask=0xFF, what=""):
            f"t_bad={res['t_bad']} (max rel {res['t_max_rel']:.2e}) bary_bad={res['bary_bad']} (max abs {res['bary_max_abs']:.2e}) "
            f"oracle {time.time() - t0:.1f} s")
     print(msg)
+    from tests.gpu_util import record_soft
+    record_soft(what, res, "see test")
     assert res["id_mismatch"] == 0, msg + f" first bad rays {res['bad_index']}"
     assert res["t_bad"] == 0 and res["bary_bad"] == 0, msg
     assert res["exact"] + res["tie"] + res["grazing"] == res["n"], msg
