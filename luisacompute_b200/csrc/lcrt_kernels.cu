@@ -885,9 +885,21 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
         __syncwarp();
     }
     for (;;) {
+        // The ballot below is meant to see the whole warp.  nvcc 12.9 lowers __ballot_sync(0xffffffff, ..) here to a VOTE / VOTEU
+        // with NO preceding WARPSYNC in some instantiations — it takes the BSYNC.RECONVERGENT in front of the back edge for
+        // convergence, turns an explicit __syncwarp() into a NOP and ignores a run-time mask — and the RayQuery instantiation of
+        // round 1, one of those, did not finish in half of its runs on C5's bounce rays (profiles/r2_trace_experiments.md §3):
+        // a part of the warp that votes on its own can never find "every lane idle" and spins for ever once the rays are
+        // exhausted.  Every build with a WARPSYNC.ALL on the back edge has always finished.  The instantiations that do not get one
+        // from the compiler are therefore written so that a PART of a warp is also correct on its own: "everybody" is whoever
+        // takes part in the vote, and the leader is its lowest lane.  (With the whole warp present: the same values as before.)
+        // Closest-hit in place and FUSED_EACH carry the WARPSYNC.ALL and keep the constants: their SASS is unchanged.
+        constexpr bool converge = MODE != MODE_CLOSEST || FUSED == FUSED_BATCH || COUNT;
+        const uint32_t here = converge ? __ballot_sync(0xffffffffu, true) : 0xffffffffu;
+        const int leader = converge ? __ffs((int)here) - 1 : 0;
         // ---- warp-cooperative retire + refill of idle lanes
         const uint32_t idle = __ballot_sync(0xffffffffu, !active);
-        if (idle && ((!exhausted && (uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN) || idle == 0xffffffffu)) {
+        if (idle && ((!exhausted && (uint32_t)__popc(idle) >= (uint32_t)LCRT_REFILL_MIN) || idle == here)) {
             if constexpr (MODE == MODE_CLOSEST && FUSED != FUSED_NONE) {
                 // the retiring lanes finish their records themselves (exact t, u, v)
                 uint64_t ray_idx = ~0ull;
@@ -973,8 +985,8 @@ __global__ void __launch_bounds__(TRACE_BLOCK, LCRT_TRACE_MIN_BLOCKS) k_trace(Tr
             const uint32_t want = (uint32_t)__popc(idle);
             if (warp_next == warp_end) {
                 unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(p.next, (unsigned long long)TRACE_BATCH);
-                base = __shfl_sync(0xffffffffu, base, 0);
+                if ((int)lane == leader) base = atomicAdd(p.next, (unsigned long long)TRACE_BATCH);
+                base = __shfl_sync(0xffffffffu, base, leader);
                 warp_next = base < p.n ? base : p.n;
                 warp_end = base + TRACE_BATCH < p.n ? base + TRACE_BATCH : p.n;
                 if constexpr (MODE == MODE_CLOSEST && FUSED == FUSED_BATCH) {
