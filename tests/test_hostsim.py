@@ -184,3 +184,59 @@ def test_ray_query(oracle):
     assert not np.any(got["inst"] == 0)
     res = oracle.compare_closest(oa, rays, got)
     assert res["id_mismatch"] == 0
+
+
+def _general_affine(rng, translate):
+    """rotation x shear x non-uniform (possibly mirroring) scale, then a translation of the given magnitude"""
+    R = S.mat_rotation(rng.normal(size=3), rng.uniform(0, 6))
+    sc = np.eye(4)
+    sc[0, 0], sc[1, 1], sc[2, 2] = rng.uniform(0.2, 3.0, 3) * rng.choice([-1, 1], 3)
+    sh = np.eye(4)
+    sh[0, 1], sh[0, 2], sh[1, 2] = rng.uniform(-0.5, 0.5, 3)
+    return S.affine_from_4x4(S.mat_translation(*(rng.uniform(-1, 1, 3) * translate)) @ R @ sh @ sc)
+
+
+def _fuzz_case(oracle, seed, translate):
+    rng = np.random.default_rng(1000 + seed)
+    verts, tris = S.triangle_soup(int(rng.integers(50, 3000)), seed=seed, s=float(rng.choice([0.01, 0.05, 0.3])))
+    n_inst = int(rng.integers(1, 7))
+    xf = [_general_affine(rng, translate) for _ in range(n_inst)]
+    oa, sa = _pair(oracle, [(verts, tris)], xf, blas_index=[0] * n_inst)
+    assert sa.validate()[0] == 0
+    n = 3000
+    rays = np.zeros(n, dtype=S.RAY_DTYPE)
+    which = rng.integers(0, n_inst, n)
+    A = np.array([np.asarray(a, dtype=np.float64).reshape(3, 4) for a in xf])
+    scale = np.abs(A[which, :, :3]).sum(axis=(1, 2))[:, None]
+    o = A[which, :, 3] + (A[which, :, :3] @ np.array([0.5, 0.5, 0.5])) + rng.normal(size=(n, 3)) * scale * 1.5
+    d = np.einsum('nij,nj->ni', A[which, :, :3], rng.uniform(0, 1, (n, 3))) + A[which, :, 3] - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    axis = rng.random(n) < 0.05                                   # some axis-parallel directions (zero components)
+    d[axis] = np.eye(3)[rng.integers(0, 3, axis.sum())] * rng.choice([-1, 1], axis.sum())[:, None]
+    rays["o"], rays["d"] = o.astype(np.float32), d.astype(np.float32)
+    rays["tmin"] = np.where(rng.random(n) < 0.3, rng.uniform(0, 1, n) * scale[:, 0], 0).astype(np.float32)
+    rays["tmax"] = np.where(rng.random(n) < 0.3, rays["tmin"] + rng.uniform(0, 3, n) * scale[:, 0], S.FLT_MAX).astype(np.float32)
+    res = oracle.compare_closest(oa, rays, sa.trace_closest(rays))
+    any_diff = int(np.count_nonzero((sa.trace_any(rays) != 0) != (oa.trace_any(rays) != 0)))
+    return res, any_diff
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_general_affine_instances_fuzz(oracle, seed):
+    """Instances under rotation x shear x non-uniform, possibly mirroring scale, translated by up to 1000 scene sizes; rays with
+    zero direction components and finite [tmin, tmax] intervals.  Ids exact outside the tie / grazing bands, t and barycentrics
+    within 1e-5 / 1e-4 of the oracle."""
+    res, any_diff = _fuzz_case(oracle, seed, [0.5, 10.0, 1000.0][seed % 3])
+    assert res["id_mismatch"] == 0 and res["t_bad"] == 0 and res["bary_bad"] == 0, res
+    assert res["tie"] + res["grazing"] <= 6 and any_diff <= res["tie"] + res["grazing"] + 1, (res, any_diff)
+
+
+@pytest.mark.xfail(reason="known limit (ADVICE r1, DESIGN.md §7): BLAS node boxes are not padded for the fp32 object-space ray error; with an "
+                          "instance 1e5 scene sizes away from the origin (fp32 world coordinates 0.008 apart, triangles 0.005 across) a few rays in "
+                          "a thousand miss a child box the exact ray touches", strict=False)
+def test_general_affine_instances_far_from_the_origin(oracle):
+    bad = 0
+    for seed in (3, 7, 15):
+        res, _ = _fuzz_case(oracle, seed, 1e5)
+        bad += res["id_mismatch"]
+    assert bad == 0, bad
