@@ -240,3 +240,33 @@ def test_general_affine_instances_far_from_the_origin(oracle):
         res, _ = _fuzz_case(oracle, seed, 1e5)
         bad += res["id_mismatch"]
     assert bad == 0, bad
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_ray_query_general_affine_fuzz(oracle, seed):
+    """RayQuery (query_all, triangle handlers commit-all / cut-out, the PROC_BOX program) over AABB primitives and meshes instanced
+    under general affine transforms, opaque and non-opaque mixed: hit type and instance exact, t within 1e-5; the primitive may
+    differ only between candidates at the same distance (overlapping boxes entered at the ray's start: the tie rule)."""
+    rng = np.random.default_rng(500 + seed)
+    aabbs = S.sphere_aabbs(int(rng.integers(8, 200)), radius=float(rng.choice([0.02, 0.1, 0.3])))
+    verts, tris = S.triangle_soup(int(rng.integers(50, 800)), seed=seed, s=0.1)
+    n_inst = int(rng.integers(2, 6))
+    xf = [_general_affine(rng, [0.5, 10.0, 1000.0][seed % 3]) for _ in range(n_inst)]
+    oa, sa = _pair(oracle, [aabbs, (verts, tris)], xf, blas_index=[int(rng.integers(0, 2)) for _ in range(n_inst)],
+                   opaque=[bool(rng.integers(0, 2)) for _ in range(n_inst)])
+    n = 2000
+    rays = np.zeros(n, dtype=S.RAY_DTYPE)
+    which = rng.integers(0, n_inst, n)
+    A = np.array([np.asarray(a, dtype=np.float64).reshape(3, 4) for a in xf])
+    scale = np.abs(A[which, :, :3]).sum(axis=(1, 2))[:, None]
+    o = A[which, :, 3] + (A[which, :, :3] @ np.array([0.5, 0.5, 0.5])) + rng.normal(size=(n, 3)) * scale * 1.5
+    d = np.einsum('nij,nj->ni', A[which, :, :3], rng.uniform(0, 1, (n, 3))) + A[which, :, 3] - o
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    rays["o"], rays["d"], rays["tmin"], rays["tmax"] = o.astype(np.float32), d.astype(np.float32), 0, S.FLT_MAX
+    for tri_prog in (0, 1):
+        e, g = oa.query(rays, 0xFF, False, tri_prog, 1), sa.query(rays, 0xFF, False, tri_prog, 1)
+        assert np.array_equal(e["hit_type"], g["hit_type"]) and np.array_equal(e["inst"], g["inst"])
+        hit = e["hit_type"] != 0
+        rel = np.abs(g["t"][hit].astype(np.float64) - e["t"][hit]) / np.maximum(np.abs(e["t"][hit]), 1e-30)
+        assert np.all(rel <= 1e-5), float(rel.max())
+        assert np.count_nonzero(e["prim"][hit] != g["prim"][hit]) <= n // 100
