@@ -167,6 +167,9 @@ struct InstInput {
             for (int k = 0; k < 12; k++) r.inv_exact[k] = 0.0;
         }
         for (int k = 0; k < 12; k++) r.inv[k] = (float)r.inv_exact[k];
+#if LCRT_RECENTER
+        for (int a = 0; a < 3; a++) memcpy(&r.spare[a], &in.affine[4 * a + 3], 4);
+#endif
         bool identity = true;
         for (int k = 0; k < 12; k++) identity = identity && in.affine[k] == ((k == 0 || k == 5 || k == 10) ? 1.f : 0.f);
         r.nodes = h ? (uint64_t)(reinterpret_cast<const char *>(h) + h->nodes_offset) : 0ull;

@@ -261,13 +261,21 @@ struct alignas(16) InstanceRecord {// 256 B = two 128-byte lines: TLAS leaf, eve
     uint32_t mask;     // visibility mask (8 bits)
     uint32_t flags;    // bits 0..7: BlasKind of the target, bit 8: opaque, bit 9: the transform is exactly the identity
     uint32_t pad;
-    uint32_t spare[12];
+    uint32_t spare[12];// LCRT_RECENTER: spare[0..2] = the instance's world translation (fp32 bits), see Traversal::setup_ray
     // ---- cold line: only the (rare) double-precision fallback of the triangle test reads it
     double inv_exact[12];// world -> object in double: the fallback re-derives the object-space ray from the world ray
                          // with it, so its decisions and t do not inherit fp32 transform rounding
     uint64_t spare2[4];
 };
 static_assert(sizeof(InstanceRecord) == 256, "InstanceRecord must be 256 bytes");
+// LCRT_RECENTER=1 (off by default: not yet measured on a GPU, it changes the traversal kernels): the object-space ray origin is
+// computed as inv_linear * (o - T) instead of inv * o + inv_translation.  With an instance far from the origin the two large
+// terms of the second form are rounded separately and cancel (error ~ |T| * 2^-24, 0.004 at |T| = 1e5); in the first form o - T is
+// exact when o and T are close (Sterbenz) and the error is relative to the SMALL difference.  tests/hostsim builds both forms;
+// tests/test_hostsim.py::test_general_affine_instances_far_from_the_origin shows the difference.
+#ifndef LCRT_RECENTER
+#define LCRT_RECENTER 0
+#endif
 constexpr uint32_t INSTANCE_FETCH_BYTES = 80;// algorithmic bytes of one instance entry (roofline)
 constexpr uint32_t IREC_KIND_MASK = 0xffu, IREC_OPAQUE = 1u << 8, IREC_IDENTITY = 1u << 9;
 

@@ -593,18 +593,35 @@ struct Traversal {
         if (blas_sp >= 0 && !(cur_flags & IREC_IDENTITY)) {
             const f4 *rec = reinterpret_cast<const f4 *>(tlas_recs + store->ldw(CW_REC));
             const f4 m0 = ldg16(rec), m1 = ldg16(rec + 1), m2 = ldg16(rec + 2);
+#if LCRT_RECENTER
+            // o' = inv_linear * (o - T): the subtraction is exact for an origin near the instance, the rest works on small numbers
+            const f4 tw = ldg16(rec + 5);// { T.x, T.y, T.z, - } as fp32 bits (InstanceRecord::spare)
+            const float rx = w0.x - tw.x, ry = w0.y - tw.y, rz = w0.z - tw.z;
+            sox = fmaf(m0.x, rx, fmaf(m0.y, ry, m0.z * rz));
+            soy = fmaf(m1.x, rx, fmaf(m1.y, ry, m1.z * rz));
+            soz = fmaf(m2.x, rx, fmaf(m2.y, ry, m2.z * rz));
+#else
             sox = fmaf(m0.x, w0.x, fmaf(m0.y, w0.y, fmaf(m0.z, w0.z, m0.w)));
             soy = fmaf(m1.x, w0.x, fmaf(m1.y, w0.y, fmaf(m1.z, w0.z, m1.w)));
             soz = fmaf(m2.x, w0.x, fmaf(m2.y, w0.y, fmaf(m2.z, w0.z, m2.w)));
+#endif
             sdx = fmaf(m0.x, w1.x, fmaf(m0.y, w1.y, m0.z * w1.z));
             sdy = fmaf(m1.x, w1.x, fmaf(m1.y, w1.y, m1.z * w1.z));
             sdz = fmaf(m2.x, w1.x, fmaf(m2.y, w1.y, m2.z * w1.z));
             // |fl(o') - o'_exact| <= 5 u * max_i (sum_j |inv_ij o_j| + |inv_i3|): entries rounded from double (1 u),
             // three FFMA roundings; likewise for the direction
+#if LCRT_RECENTER
+            // |o - T| is within u of exact (exact when the two are within a factor of two); the entries and three roundings as below
+            const float ax = fabsf(rx), ay = fabsf(ry), az = fabsf(rz);
+            const float mx = 1.25f * fmaf(fabsf(m0.x), ax, fmaf(fabsf(m0.y), ay, fabsf(m0.z) * az));
+            const float my = 1.25f * fmaf(fabsf(m1.x), ax, fmaf(fabsf(m1.y), ay, fabsf(m1.z) * az));
+            const float mz = 1.25f * fmaf(fabsf(m2.x), ax, fmaf(fabsf(m2.y), ay, fabsf(m2.z) * az));
+#else
             const float ax = fabsf(w0.x), ay = fabsf(w0.y), az = fabsf(w0.z);
             const float mx = fmaf(fabsf(m0.x), ax, fmaf(fabsf(m0.y), ay, fmaf(fabsf(m0.z), az, fabsf(m0.w))));
             const float my = fmaf(fabsf(m1.x), ax, fmaf(fabsf(m1.y), ay, fmaf(fabsf(m1.z), az, fabsf(m1.w))));
             const float mz = fmaf(fabsf(m2.x), ax, fmaf(fabsf(m2.y), ay, fmaf(fabsf(m2.z), az, fabsf(m2.w))));
+#endif
             const float bx = fabsf(w1.x), by = fabsf(w1.y), bz = fabsf(w1.z);
             const float nx = fmaf(fabsf(m0.x), bx, fmaf(fabsf(m0.y), by, fabsf(m0.z) * bz));
             const float ny = fmaf(fabsf(m1.x), bx, fmaf(fabsf(m1.y), by, fabsf(m1.z) * bz));

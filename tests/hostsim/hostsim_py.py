@@ -17,11 +17,32 @@ BUILD_ALLOW_UPDATE = 2
 DEFAULT_CI = 0.5
 
 
+_LIB_NAME = "libhostsim.so"
+
+
+class variant:
+    """with variant("libhostsim_recenter.so"): ...  — the same simulation built with other compile-time options (tests/hostsim/Makefile)"""
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        global _LIB, _LIB_NAME
+        self.saved = (_LIB, _LIB_NAME)
+        _LIB, _LIB_NAME = None, self.name
+        return self
+
+    def __exit__(self, *exc):
+        global _LIB, _LIB_NAME
+        _LIB, _LIB_NAME = self.saved
+        return False
+
+
 def lib():
     global _LIB
     if _LIB is None:
         subprocess.check_call(["make", "-C", _HERE, "-s"])
-        L = C.CDLL(os.path.join(_HERE, "libhostsim.so"))
+        L = C.CDLL(os.path.join(_HERE, _LIB_NAME))
         vp, u32, u64, f32, ci = C.c_void_p, C.c_uint32, C.c_uint64, C.c_float, C.c_int
         L.hs_blob_layout.argtypes = [u32, u32, u32, vp]
         L.hs_build_triangles.restype = ci

@@ -231,15 +231,20 @@ def test_general_affine_instances_fuzz(oracle, seed):
     assert res["tie"] + res["grazing"] <= 6 and any_diff <= res["tie"] + res["grazing"] + 1, (res, any_diff)
 
 
-@pytest.mark.xfail(reason="known limit (ADVICE r1, DESIGN.md §7): BLAS node boxes are not padded for the fp32 object-space ray error; with an "
-                          "instance 1e5 scene sizes away from the origin (fp32 world coordinates 0.008 apart, triangles 0.005 across) a few rays in "
-                          "a thousand miss a child box the exact ray touches", strict=False)
-def test_general_affine_instances_far_from_the_origin(oracle):
-    bad = 0
-    for seed in (3, 7, 15):
-        res, _ = _fuzz_case(oracle, seed, 1e5)
-        bad += res["id_mismatch"]
-    assert bad == 0, bad
+def test_general_affine_instances_far_from_the_origin(oracle, schedule):
+    """ADVICE r1 / DESIGN.md §7: with an instance 1e5 scene sizes away from the origin (fp32 world coordinates 0.008 apart, triangles
+    0.005 across) the SHIPPED transform of the ray into instance space (inv * o + inv_translation: two large terms rounded
+    separately) loses a few rays in a thousand — a child box the exact ray touches is missed.  The re-centred form (inv_linear *
+    (o - T), LCRT_RECENTER=1, built here as libhostsim_recenter.so) does not.  It is off in the product until it has been measured
+    on a GPU (it changes the traversal kernels); this test keeps both facts on record."""
+    shipped = sum(_fuzz_case(oracle, seed, 1e5)[0]["id_mismatch"] for seed in (3, 7, 15))
+    with H.variant("libhostsim_recenter.so"):
+        H.lib().hs_set_defer(schedule)
+        recentred = [_fuzz_case(oracle, seed, 1e5) for seed in (3, 7, 15, 19, 23)]
+    assert shipped > 0, "the shipped transform no longer shows the limit: make LCRT_RECENTER the default or drop this test"
+    for res, any_diff in recentred:
+        assert res["id_mismatch"] == 0 and res["t_bad"] == 0 and res["bary_bad"] == 0, res
+        assert any_diff <= res["tie"] + res["grazing"] + 1, (res, any_diff)
 
 
 @pytest.mark.parametrize("seed", range(4))
